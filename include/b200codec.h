@@ -1,0 +1,182 @@
+/*
+ * b200codec.h -- C ABI of the B200-native (sm_100a) xcodec2-compatible codec DECODE path.
+ *
+ * This is the drop-in boundary for tts-max's `tts.core.codec.decoding` /
+ * `tts.core.codec.decoder.Decoder.forward`. The reference is pure Python and has no FFI;
+ * each entry point below names the reference interface it replaces (paths relative to the
+ * reference repo root). The Python mirror of the reference interface
+ * (tts_max_b200/codec/{decoding,decoder}.py) is a thin ctypes client of this header.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns 0 on success, non-zero on failure; the message is available
+ *     from b200codec_last_error() (thread-local). The library never aborts the process:
+ *     the reference's callers rely on catchable exceptions
+ *     (tts/training/rlhf/rewards.py:86-97).
+ *   - the caller owns every input/output buffer and the CUDA stream; the library owns only
+ *     the prepared weights and its activation workspace.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
+ *     ordinary (ideally pinned) host memory.
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef B200CODEC_H_
+#define B200CODEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define B200CODEC_ABI_VERSION 1
+
+/* arithmetic type of the tensor-core operands (accumulation is always fp32; the residual
+ * stream, norms, softmax, FSQ lookup and ISTFT are always fp32). */
+enum B200CodecPrecision {
+    B200CODEC_BF16 = 0, /* tcgen05 kind::f16, bf16 operands (BASELINE config 2 "bf16 decode") */
+    B200CODEC_FP16 = 1, /* tcgen05 kind::f16, fp16 operands (same rate, 3 more mantissa bits) */
+    B200CODEC_TF32 = 2  /* tcgen05 kind::tf32, fp32 storage (half rate; "fp32-tolerance" mode) */
+};
+
+/* element type of the ids passed to the lookup / decode entry points */
+enum B200CodecIdType { B200CODEC_IDS_I32 = 0, B200CODEC_IDS_I64 = 1 };
+
+/* dtype tags for b200codec_load_tensor */
+enum B200CodecDType { B200CODEC_F32 = 0, B200CODEC_F16 = 1, B200CODEC_BF16_T = 2, B200CODEC_F64 = 3 };
+
+/* Mirrors the constructor arguments of `Decoder` (tts/core/codec/decoder.py:17-37) and
+ * `DecoderConfig` (tts/core/codec/decoding.py:13-35). */
+typedef struct B200CodecConfig {
+    int32_t abi_version;      /* must be B200CODEC_ABI_VERSION */
+    int32_t sample_rate;      /* 16000 for xcodec2 */
+    int32_t hop_length;       /* 320; n_fft = win = 4 * hop (decoder_modules.py:426-431) */
+    int32_t n_upsample;       /* len(upsample_factors); must be 0 (upsampler is a NEXT row) */
+    int32_t precision;        /* enum B200CodecPrecision */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t hidden_dim;       /* 1024 */
+    int32_t depth;            /* 12 transformer blocks */
+    int32_t heads;            /* 16 */
+    int32_t vq_dim;           /* 2048 */
+    int32_t reserved[6];
+} B200CodecConfig;
+
+typedef struct B200Codec B200Codec;
+
+/* thread-local message of the last failing call ("" if none) */
+const char* b200codec_last_error(void);
+
+/* number of state-dict tensors the decoder expects (117 for the xcodec2 config) and the
+ * i-th expected key ("decoder.quantizer.project_out.weight", ...), in the order of
+ * `Decoder.state_dict()`. Used by the Python shim for strict loading
+ * (tts/core/codec/decoder.py:109-110,119). */
+int b200codec_num_tensors(const B200Codec* h);
+const char* b200codec_tensor_key(const B200Codec* h, int i);
+/* shape of the i-th expected tensor; returns ndim (<= 4) */
+int b200codec_tensor_shape(const B200Codec* h, int i, int64_t shape_out[4]);
+
+/* Replaces Decoder.__init__ (tts/core/codec/decoder.py:17-67): validates the 50 Hz
+ * constraint (:31-37), allocates the module. Weights are NOT initialised. */
+int b200codec_create(const B200CodecConfig* cfg, B200Codec** out);
+void b200codec_destroy(B200Codec* h);
+
+/* Replaces load_state_dict for one tensor (tts/core/codec/decoder.py:91-119 keeps the two
+ * checkpoint layouts in Python and calls this once per `Decoder.state_dict()` key).
+ * `host_ptr` is contiguous host memory of `dtype`; unknown keys and shape mismatches fail
+ * (strict=True semantics). */
+int b200codec_load_tensor(B200Codec* h, const char* key, const void* host_ptr, int dtype,
+                          const int64_t* shape, int ndim);
+
+/* Reads the fp32 master copy of a tensor back (state_dict() round trip). */
+int b200codec_read_tensor(const B200Codec* h, const char* key, float* host_out, size_t n_elems);
+
+/* Fails unless every expected tensor has been loaded; repacks weights for the tensor cores
+ * (operand dtype, conv taps -> K-major slabs, head-indexed RoPE folded into c_attn
+ * (decoder_modules.py:280-281), TMA descriptors). Idempotent. */
+int b200codec_finalize_weights(B200Codec* h, void* stream);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+
+/* Replaces Decoder.forward (tts/core/codec/decoder.py:69-89) for a VARLEN batch: utterance
+ * u has seqlens_host[u] tokens, ids are packed back to back, waveforms are packed back to
+ * back with hop_length * seqlens[u] samples each. Every utterance is decoded with exactly
+ * the single-utterance semantics of the reference (per-utterance GroupNorm statistics,
+ * unmasked attention within the utterance, zero conv padding at the utterance edges), so an
+ * equal-length batch reproduces the reference's batched forward row for row.
+ * Asynchronous on `stream`. */
+int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
+                            const int32_t* seqlens_host, int n_utts, float* wav_dev,
+                            void* stream);
+
+/* Same, HOST buffers in and out: the call a serving loop makes
+ * (AudioDecoder.decode, tts/core/codec/decoding.py:84-89: ids .to(device) ... .cpu()).
+ * H2D of the ids, the decode, D2H of the PCM and the final synchronisation all happen
+ * inside. ids are range-checked ([0, 65535]) on the host before anything is launched. */
+int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
+                          const int32_t* seqlens_host, int n_utts, float* wav_host,
+                          void* stream);
+
+/* decode_varlen is asynchronous and takes DEVICE ids, so it cannot range-check them before
+ * launching: the FSQ kernel flags ids outside [0, 65535] (and masks them to 16 bits).
+ * After synchronising the stream, this returns 1 if any decode since the last call saw such
+ * an id (and clears the flag). decode_host checks on the host instead and fails up front. */
+int b200codec_take_id_error(B200Codec* h);
+
+/* number of kernels the library launched since creation (bench.py's gpu_launches) */
+int64_t b200codec_launch_count(const B200Codec* h);
+
+/* Per-stage timing hook: when enabled (on != 0) decode calls record CUDA events around
+ * every stage; b200codec_stage_times returns the accumulated device milliseconds per stage
+ * name since the last reset. Adds synchronisation; never enable it inside a timed run. */
+int b200codec_profile(B200Codec* h, int on);
+int b200codec_stage_times(B200Codec* h, int max_stages, const char** names_out,
+                          float* ms_out, int* n_out);
+
+/* ---- per-stage entry points (unit parity against the oracle) ------------------------- */
+
+/* K1, ResidualFSQ.get_output_from_indices (vector-quantize-pytorch 1.17.8; called at
+ * tts/core/codec/decoder.py:77): n ids -> [n, 2048] fp32, bit-exact with torch CPU
+ * (acc = 0; acc += code_k * W[c,k], k = 0..7; + bias[c]). */
+int b200codec_fsq_lookup(B200Codec* h, const void* ids_dev, int id_type, int64_t n,
+                         float* out_dev, void* stream);
+
+/* K13+K14, ISTFTHead.forward after the Linear + ISTFT.forward "same"
+ * (tts/core/codec/decoder_modules.py:131-148, 35-93): x_pred_dev is the head Linear output,
+ * packed [sum(T), ld] fp32 (cols 0..640 log-magnitude, 641..1281 phase); writes
+ * hop*T samples per utterance. */
+int b200codec_istft(B200Codec* h, const float* x_pred_dev, int ld, const int32_t* seqlens_host,
+                    int n_utts, float* wav_dev, void* stream);
+
+/* Generic tensor-core GEMM / implicit conv1d used by every dense layer of the path
+ * (see csrc/gemm_tc05.cuh). a: [M, Cin] operand dtype (per `precision`), w: [N, taps*Cin]
+ * same dtype, out: [M, ldc] (out_dtype: 0 = fp32, 1 = operand dtype).
+ * out = act(conv(a, w) + bias) + residual. */
+int b200codec_gemm(int precision, const void* a_dev, const void* w_dev, int M, int N, int Cin,
+                   int taps, void* out_dev, int out_dtype, int ldc, const float* bias_dev,
+                   const float* residual_dev, int ld_res, int act, void* stream);
+
+/* RMSNorm / LayerNorm / GroupNorm(32)+swish on token-major [rows, 1024] fp32 input, output
+ * in the operand dtype of `precision` (decoder_modules.py:226-236, 373, 151-159). */
+int b200codec_rmsnorm(int precision, const float* x_dev, const float* w_dev, int rows, int dim,
+                      float eps, void* out_dev, void* stream);
+int b200codec_layernorm(int precision, const float* x_dev, const float* w_dev, const float* b_dev,
+                        int rows, int dim, float eps, void* out_dev, void* stream);
+int b200codec_groupnorm_swish(int precision, const float* x_dev, const float* gamma_dev,
+                              const float* beta_dev, const int32_t* seqlens_host, int n_utts,
+                              int dim, float eps, void* out_dev, void* stream);
+
+/* Unmasked multi-head attention over packed varlen utterances (decoder_modules.py:283-285):
+ * qkv [sum(T), 3*H*64] operand dtype, rows "(r h d)"; out [sum(T), H*64]. */
+int b200codec_attention(int precision, const void* qkv_dev, const int32_t* seqlens_host,
+                        int n_utts, int heads, void* out_dev, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CODEC_H_ */

@@ -1,0 +1,997 @@
+// b200codec: handle, weights, workspace, the decode forward pass and the C ABI (include/b200codec.h).
+//
+// Forward pass == Decoder.forward (tts/core/codec/decoder.py:69-89) ->
+// VocosBackbone.forward (tts/core/codec/decoder_modules.py:390-400) ->
+// ISTFTHead.forward (:118-148), restructured for B200:
+//   * activations are token-major [rows, C] in one PADDED ROW SPACE for the whole varlen batch
+//     (3 zero rows between utterances), so every Linear is a plain GEMM over all rows, every
+//     Conv1d is the same GEMM kernel with row-shifted K-slabs, and the transposes of
+//     :391,395,397,399 disappear;
+//   * GEMM operands are 16-bit (bf16 / fp16) with fp32 accumulation in TMEM; the residual
+//     stream, all norm statistics, softmax, the FSQ lookup and the ISTFT stay fp32;
+//   * bias / SiLU / residual-add / halo masking live in the GEMM epilogue.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200codec.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+static thread_local char g_err[1024] = {0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr int kGap = 3;          // zero rows between utterances (conv7 halo)
+constexpr int kHeadLd = 1344;    // head.out columns padded to a multiple of 32 (1282 -> 1344)
+
+struct TensorSpec {
+    std::string key;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto d : shape) n *= static_cast<size_t>(d);
+        return n;
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        // grow geometrically so varlen batches of similar size do not thrash the allocator
+        size_t want = need + need / 4;
+        B200_CUDA_OK(cudaMalloc(&p, want));
+        bytes = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+struct ResBlockW {
+    const float *gn1_w, *gn1_b, *b1, *gn2_w, *gn2_b, *b2;
+    void *w1, *w2;  // operand dtype [1024, 3*1024]
+};
+struct LayerW {
+    const float *att_norm, *ffn_norm;
+    void *qkv, *proj, *fc1, *fc2;
+};
+
+struct StageTimer {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+struct B200Codec {
+    B200CodecConfig cfg;
+    int C, H, L, V, hop, n_fft, n_bins;
+    std::vector<TensorSpec> specs;
+    std::map<std::string, int> index;
+    std::vector<float*> master;  // fp32 device copies, nullptr until loaded
+    bool finalized = false;
+
+    // prepared weights
+    DevBuf wbuf;        // one slab for all operand-dtype weights
+    void* w_fc = nullptr;
+    void* w_embed = nullptr;
+    ResBlockW res[4];
+    LayerW layers[64];
+    void* w_head = nullptr;
+    float* head_bias_pad = nullptr;
+    float2* twiddle = nullptr;
+    float *rope_cos = nullptr, *rope_sin = nullptr;
+
+    // workspace (grow-only)
+    DevBuf ws;
+    int ws_rows = 0;
+    void *a0, *xc, *an, *qkv, *y, *f;  // operand dtype
+    float *x, *hbuf, *ho;
+    double* gn_stats = nullptr;
+    size_t gn_stats_bytes = 0;
+    // plan (row space) cache
+    DevBuf plan_dev;
+    void* plan_host = nullptr;
+    size_t plan_host_bytes = 0;
+    std::vector<int32_t> plan_key;
+    int plan_gap = -1;
+    RowSpace rs;
+    // io staging for decode_host
+    DevBuf io_ids, io_wav;
+    int* err_flag_host = nullptr;  // mapped pinned
+    int* err_flag_dev = nullptr;
+
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<StageTimer> timers;
+    std::map<std::string, float> stage_ms;
+    std::vector<std::string> stage_order;
+
+    const float* m(const std::string& key) const {
+        auto it = index.find(key);
+        return it == index.end() ? nullptr : master[it->second];
+    }
+};
+
+namespace {
+
+void add_spec(B200Codec* h, const std::string& key, std::vector<int64_t> shape) {
+    h->index[key] = static_cast<int>(h->specs.size());
+    h->specs.push_back({key, std::move(shape)});
+}
+
+void build_specs(B200Codec* h) {
+    const int64_t C = h->C, V = h->V;
+    const std::string g = "decoder.";
+    add_spec(h, g + "quantizer.project_in.weight", {8, V});
+    add_spec(h, g + "quantizer.project_in.bias", {8});
+    add_spec(h, g + "quantizer.project_out.weight", {V, 8});
+    add_spec(h, g + "quantizer.project_out.bias", {V});
+    add_spec(h, g + "backbone.embed.weight", {C, C, 7});
+    add_spec(h, g + "backbone.embed.bias", {C});
+    auto resnet = [&](const std::string& p) {
+        add_spec(h, p + "norm1.weight", {C});
+        add_spec(h, p + "norm1.bias", {C});
+        add_spec(h, p + "conv1.weight", {C, C, 3});
+        add_spec(h, p + "conv1.bias", {C});
+        add_spec(h, p + "norm2.weight", {C});
+        add_spec(h, p + "norm2.bias", {C});
+        add_spec(h, p + "conv2.weight", {C, C, 3});
+        add_spec(h, p + "conv2.bias", {C});
+    };
+    resnet(g + "backbone.prior_net.0.");
+    resnet(g + "backbone.prior_net.1.");
+    for (int l = 0; l < h->L; ++l) {
+        const std::string p = g + "backbone.transformers." + std::to_string(l) + ".";
+        add_spec(h, p + "att_norm.weight", {C});
+        add_spec(h, p + "ffn_norm.weight", {C});
+        add_spec(h, p + "att.c_attn.weight", {3 * C, C});
+        add_spec(h, p + "att.c_proj.weight", {C, C});
+        add_spec(h, p + "mlp.fc1.weight", {4 * C, C});
+        add_spec(h, p + "mlp.fc2.weight", {C, 4 * C});
+    }
+    add_spec(h, g + "backbone.final_layer_norm.weight", {C});
+    add_spec(h, g + "backbone.final_layer_norm.bias", {C});
+    resnet(g + "backbone.post_net.0.");
+    resnet(g + "backbone.post_net.1.");
+    add_spec(h, g + "head.out.weight", {h->n_fft + 2, C});
+    add_spec(h, g + "head.out.bias", {h->n_fft + 2});
+    add_spec(h, g + "head.istft.window", {h->n_fft});
+    add_spec(h, "fc_post_a.weight", {C, V});
+    add_spec(h, "fc_post_a.bias", {C});
+}
+
+// ---------------------------------------------------------------------------
+// row-space plan
+// ---------------------------------------------------------------------------
+struct PlanLayout {
+    size_t R = 0;
+    int n_utts = 0;
+    int64_t toks = 0;
+    int max_len = 0;
+    int64_t n_attn = 0, n_istft = 0;
+    size_t off_row_tok, off_row_utt, off_u0, off_ul, off_ut, off_attn, off_istft, off_valid;
+    size_t total_bytes = 0;
+};
+
+int plan_layout(const int32_t* seqlens, int n_utts, int gap, PlanLayout* L) {
+    B200_CHECK(n_utts > 0, "decode: empty batch (no utterances)");
+    int64_t rows = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        const int T = seqlens[u];
+        B200_CHECK(T > 0, "decode: utterance %d is empty (length %d); the reference's callers "
+                   "guard T == 0 (rewards.py:76-82)", u, T);
+        rows += T + (u + 1 < n_utts ? gap : 0);
+        L->toks += T;
+        L->max_len = T > L->max_len ? T : L->max_len;
+        L->n_attn += (T + kAttnBlockQ - 1) / kAttnBlockQ;
+        L->n_istft += (T + kIstftOutHops - 1) / kIstftOutHops;
+    }
+    B200_CHECK(rows < (1 << 30), "decode: batch too large (%lld rows)", (long long)rows);
+    const size_t R = static_cast<size_t>(rows);
+    L->R = R;
+    L->n_utts = n_utts;
+    // layout (int32 units): row_tok[R] row_utt[R] utt_row0[n] utt_len[n] utt_tok0[n]
+    //                       attn_work[4*n_attn] istft_work[4*n_istft] row_valid[R bytes]
+    L->off_row_tok = 0;
+    L->off_row_utt = R;
+    L->off_u0 = 2 * R;
+    L->off_ul = 2 * R + n_utts;
+    L->off_ut = 2 * R + 2 * n_utts;
+    L->off_attn = (2 * R + 3 * n_utts + 3) & ~static_cast<size_t>(3);  // int4 aligned
+    L->off_istft = L->off_attn + 4 * L->n_attn;
+    L->off_valid = L->off_istft + 4 * L->n_istft;
+    L->total_bytes = (L->off_valid * 4 + R + 255) & ~static_cast<size_t>(255);
+    return 0;
+}
+
+void plan_fill(const PlanLayout& L, const int32_t* seqlens, int gap, void* host) {
+    int32_t* hp = static_cast<int32_t*>(host);
+    uint8_t* hv = reinterpret_cast<uint8_t*>(hp + L.off_valid);
+    // work items of one utterance are contiguous, which keeps its K/V in L2 while its
+    // query tiles run.
+    int64_t r = 0, t0 = 0, ia = 0, ii = 0;
+    for (int u = 0; u < L.n_utts; ++u) {
+        const int T = seqlens[u];
+        hp[L.off_u0 + u] = static_cast<int32_t>(r);
+        hp[L.off_ul + u] = T;
+        hp[L.off_ut + u] = static_cast<int32_t>(t0);
+        for (int t = 0; t < T; ++t) {
+            hp[L.off_row_tok + r + t] = static_cast<int32_t>(t0 + t);
+            hp[L.off_row_utt + r + t] = u;
+            hv[r + t] = 1;
+        }
+        for (int q0 = 0; q0 < T; q0 += kAttnBlockQ) {
+            int32_t* w = hp + L.off_attn + 4 * ia++;
+            w[0] = static_cast<int32_t>(r); w[1] = T; w[2] = q0; w[3] = 0;
+        }
+        for (int b0 = 0; b0 < T; b0 += kIstftOutHops) {
+            int32_t* w = hp + L.off_istft + 4 * ii++;
+            w[0] = u; w[1] = b0; w[2] = 0; w[3] = 0;
+        }
+        r += T;
+        t0 += T;
+        if (u + 1 < L.n_utts)
+            for (int gi = 0; gi < gap; ++gi, ++r) {
+                hp[L.off_row_tok + r] = -1;
+                hp[L.off_row_utt + r] = -1;
+                hv[r] = 0;
+            }
+    }
+}
+
+void plan_bind(const PlanLayout& L, const void* dev, RowSpace* rs) {
+    const int32_t* dp = static_cast<const int32_t*>(dev);
+    rs->rows = static_cast<int>(L.R);
+    rs->n_utts = L.n_utts;
+    rs->total_tokens = static_cast<int>(L.toks);
+    rs->max_len = L.max_len;
+    rs->row_tok = dp + L.off_row_tok;
+    rs->row_utt = dp + L.off_row_utt;
+    rs->utt_row0 = dp + L.off_u0;
+    rs->utt_len = dp + L.off_ul;
+    rs->utt_tok0 = dp + L.off_ut;
+    rs->attn_work = reinterpret_cast<const int4*>(dp + L.off_attn);
+    rs->n_attn_work = static_cast<int>(L.n_attn);
+    rs->istft_work = reinterpret_cast<const int4*>(dp + L.off_istft);
+    rs->n_istft_work = static_cast<int>(L.n_istft);
+    rs->row_valid = reinterpret_cast<const uint8_t*>(dp + L.off_valid);
+}
+
+int build_plan(B200Codec* h, const int32_t* seqlens, int n_utts, int gap, cudaStream_t stream) {
+    B200_CHECK(n_utts > 0, "decode: empty batch (no utterances)");
+    bool same = h->plan_gap == gap && static_cast<int>(h->plan_key.size()) == n_utts &&
+                std::memcmp(h->plan_key.data(), seqlens, sizeof(int32_t) * n_utts) == 0;
+    if (same) return 0;
+    PlanLayout L;
+    if (plan_layout(seqlens, n_utts, gap, &L)) return 1;
+    if (L.total_bytes > h->plan_host_bytes) {
+        if (h->plan_host) cudaFreeHost(h->plan_host);
+        h->plan_host = nullptr;
+        h->plan_host_bytes = 0;
+        B200_CUDA_OK(cudaMallocHost(&h->plan_host, L.total_bytes * 2));
+        h->plan_host_bytes = L.total_bytes * 2;
+    }
+    // the previous plan may still be in use by work in flight on the stream
+    B200_CUDA_OK(cudaStreamSynchronize(stream));
+    if (h->plan_dev.ensure(L.total_bytes)) return 1;
+    plan_fill(L, seqlens, gap, h->plan_host);
+    B200_CUDA_OK(cudaMemcpyAsync(h->plan_dev.p, h->plan_host, L.total_bytes, cudaMemcpyHostToDevice,
+                                 stream));
+    B200_CUDA_OK(cudaStreamSynchronize(stream));  // plan_host is reused by the next build
+    plan_bind(L, h->plan_dev.p, &h->rs);
+    h->plan_key.assign(seqlens, seqlens + n_utts);
+    h->plan_gap = gap;
+    return 0;
+}
+
+// throw-away packed (gap = 0) row space for the per-stage entry points
+struct TempPlan {
+    void* dev = nullptr;
+    RowSpace rs;
+    int build(const int32_t* seqlens, int n_utts, cudaStream_t s) {
+        PlanLayout L;
+        if (plan_layout(seqlens, n_utts, 0, &L)) return 1;
+        std::vector<uint8_t> host(L.total_bytes, 0);
+        plan_fill(L, seqlens, 0, host.data());
+        B200_CUDA_OK(cudaMalloc(&dev, L.total_bytes));
+        B200_CUDA_OK(cudaMemcpyAsync(dev, host.data(), L.total_bytes, cudaMemcpyHostToDevice, s));
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        plan_bind(L, dev, &rs);
+        return 0;
+    }
+    ~TempPlan() {
+        if (dev) cudaFree(dev);
+    }
+};
+
+int ensure_workspace(B200Codec* h, int rows) {
+    if (rows <= h->ws_rows) return 0;
+    const size_t R = static_cast<size_t>(rows) + rows / 4 + 128;
+    const size_t es = operand_bytes(h->cfg.precision);
+    const size_t C = h->C;
+    auto al = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
+    size_t sz_a0 = al(R * h->V * es), sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
+           sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(R * kHeadLd * 4);
+    size_t total = sz_a0 + 3 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho;
+    h->ws.release();
+    h->ws_rows = 0;
+    if (h->ws.ensure(total)) return 1;
+    B200_CUDA_OK(cudaMemset(h->ws.p, 0, h->ws.bytes));  // no NaN garbage in halo rows
+    uint8_t* p = h->ws.as<uint8_t>();
+    h->a0 = p; p += sz_a0;
+    h->xc = p; p += sz_c;
+    h->an = p; p += sz_c;
+    h->y = p; p += sz_c;
+    h->qkv = p; p += sz_qkv;
+    h->f = p; p += sz_f;
+    h->x = reinterpret_cast<float*>(p); p += sz_x;
+    h->hbuf = reinterpret_cast<float*>(p); p += sz_x;
+    h->ho = reinterpret_cast<float*>(p); p += sz_ho;
+    h->ws_rows = static_cast<int>(R);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// profiling helpers
+// ---------------------------------------------------------------------------
+struct Stage {
+    B200Codec* h;
+    cudaStream_t s;
+    bool on;
+    Stage(B200Codec* h_, const char* name, cudaStream_t s_) : h(h_), s(s_), on(h_->profiling) {
+        if (!on) return;
+        StageTimer t;
+        t.name = name;
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, s);
+        h->timers.push_back(t);
+    }
+    ~Stage() {
+        if (on) cudaEventRecord(h->timers.back().b, s);
+    }
+};
+
+void collect_timers(B200Codec* h) {
+    for (auto& t : h->timers) {
+        cudaEventSynchronize(t.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        if (h->stage_ms.find(t.name) == h->stage_ms.end()) h->stage_order.push_back(t.name);
+        h->stage_ms[t.name] += ms;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    h->timers.clear();
+}
+
+// ---------------------------------------------------------------------------
+// the forward pass
+// ---------------------------------------------------------------------------
+#define RUN(expr)                \
+    do {                         \
+        if ((expr) != 0) return 1; \
+        h->launches++;           \
+    } while (0)
+
+int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
+         bool out_fp32, int ldc, int n_store, const float* bias, const float* residual, int act,
+         bool mask_rows, cudaStream_t s) {
+    GemmCall c;
+    c.precision = h->cfg.precision;
+    c.a = a;
+    c.a_rows = h->rs.rows;
+    c.Cin = Cin;
+    c.w = w;
+    c.N = N;
+    c.taps = taps;
+    c.out = out;
+    c.out_fp32 = out_fp32 ? 1 : 0;
+    c.ldc = ldc;
+    c.n_store = n_store;
+    c.bias = bias;
+    c.residual = residual;
+    c.ld_res = ldc;
+    c.row_valid = mask_rows ? h->rs.row_valid : nullptr;
+    c.act = act;
+    c.row_sumsq = nullptr;
+    return launch_gemm(c, s);
+}
+
+int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t s) {
+    const int C = h->C, prec = h->cfg.precision;
+    const RowSpace& rs = h->rs;
+    double* st1 = h->gn_stats + static_cast<size_t>(stats_slot) * rs.n_utts * 64;
+    double* st2 = st1 + static_cast<size_t>(rs.n_utts) * 64;
+    {
+        Stage t(h, "groupnorm_swish", s);
+        RUN(launch_groupnorm_stats(h->x, rs, C, st1, s));
+        RUN(launch_groupnorm_apply_swish(prec, h->x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, h->an, s));
+    }
+    {
+        Stage t(h, "conv3_gemm", s);
+        RUN(gemm(h, h->an, C, w.w1, C, 3, h->hbuf, true, C, C, w.b1, nullptr, kActNone, false, s));
+    }
+    {
+        Stage t(h, "groupnorm_swish", s);
+        RUN(launch_groupnorm_stats(h->hbuf, rs, C, st2, s));
+        RUN(launch_groupnorm_apply_swish(prec, h->hbuf, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, h->an, s));
+    }
+    {
+        Stage t(h, "conv3_gemm", s);
+        RUN(gemm(h, h->an, C, w.w2, C, 3, h->x, true, C, C, w.b2, h->x, kActNone, false, s));
+    }
+    return 0;
+}
+
+int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s) {
+    const int C = h->C, prec = h->cfg.precision;
+    const RowSpace& rs = h->rs;
+    B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * 8 * rs.n_utts * 64, s));
+    {
+        Stage t(h, "fsq_lookup", s);
+        RUN(launch_fsq_lookup(ids_dev, id_type, rs.row_tok, rs.rows,
+                              h->m("decoder.quantizer.project_out.weight"),
+                              h->m("decoder.quantizer.project_out.bias"), h->V, h->a0, h->V, prec,
+                              h->err_flag_dev, s));
+    }
+    {
+        Stage t(h, "fc_post_a_gemm", s);
+        // halo rows are written as zeros: this is the conv7 operand
+        RUN(gemm(h, h->a0, h->V, h->w_fc, C, 1, h->xc, false, C, C, h->m("fc_post_a.bias"),
+                 nullptr, kActNone, true, s));
+    }
+    {
+        Stage t(h, "embed_conv7_gemm", s);
+        RUN(gemm(h, h->xc, C, h->w_embed, C, 7, h->x, true, C, C,
+                 h->m("decoder.backbone.embed.bias"), nullptr, kActNone, false, s));
+    }
+    if (resnet_block(h, h->res[0], 0, s)) return 1;
+    if (resnet_block(h, h->res[1], 2, s)) return 1;
+    for (int l = 0; l < h->L; ++l) {
+        const LayerW& w = h->layers[l];
+        {
+            Stage t(h, "rmsnorm", s);
+            RUN(launch_rmsnorm(prec, h->x, w.att_norm, rs.rows, C, 1e-6f, h->an, s));
+        }
+        {
+            Stage t(h, "qkv_gemm", s);
+            RUN(gemm(h, h->an, C, w.qkv, 3 * C, 1, h->qkv, false, 3 * C, 3 * C, nullptr, nullptr,
+                     kActNone, false, s));
+        }
+        {
+            Stage t(h, "attention", s);
+            RUN(launch_attention(prec, h->qkv, rs, h->H, h->y, s));
+        }
+        {
+            Stage t(h, "proj_gemm", s);
+            RUN(gemm(h, h->y, C, w.proj, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s));
+        }
+        {
+            Stage t(h, "rmsnorm", s);
+            RUN(launch_rmsnorm(prec, h->x, w.ffn_norm, rs.rows, C, 1e-6f, h->an, s));
+        }
+        {
+            Stage t(h, "fc1_gemm", s);
+            RUN(gemm(h, h->an, C, w.fc1, 4 * C, 1, h->f, false, 4 * C, 4 * C, nullptr, nullptr,
+                     kActSilu, false, s));
+        }
+        {
+            Stage t(h, "fc2_gemm", s);
+            RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s));
+        }
+    }
+    if (resnet_block(h, h->res[2], 4, s)) return 1;
+    if (resnet_block(h, h->res[3], 6, s)) return 1;
+    {
+        Stage t(h, "layernorm", s);
+        RUN(launch_layernorm(prec, h->x, h->m("decoder.backbone.final_layer_norm.weight"),
+                             h->m("decoder.backbone.final_layer_norm.bias"), rs.rows, C, 1e-6f,
+                             h->an, s));
+    }
+    {
+        Stage t(h, "head_gemm", s);
+        RUN(gemm(h, h->an, C, h->w_head, h->n_fft + 2, 1, h->ho, true, kHeadLd, kHeadLd,
+                 h->head_bias_pad, nullptr, kActNone, false, s));
+    }
+    {
+        Stage t(h, "istft", s);
+        IstftTables tab;
+        tab.twiddle = h->twiddle;
+        tab.window = h->m("decoder.head.istft.window");
+        RUN(launch_istft(h->ho, kHeadLd, rs, tab, h->hop, wav_dev, s));
+    }
+    return 0;
+}
+
+int check_ids_host(const void* ids, int id_type, int64_t n) {
+    if (id_type == B200CODEC_IDS_I64) {
+        const int64_t* p = static_cast<const int64_t*>(ids);
+        for (int64_t i = 0; i < n; ++i)
+            B200_CHECK(p[i] >= 0 && p[i] <= 65535, "speech id %lld at position %lld is outside "
+                       "[0, 65535]", (long long)p[i], (long long)i);
+    } else {
+        const int32_t* p = static_cast<const int32_t*>(ids);
+        for (int64_t i = 0; i < n; ++i)
+            B200_CHECK(p[i] >= 0 && p[i] <= 65535, "speech id %d at position %lld is outside "
+                       "[0, 65535]", p[i], (long long)i);
+    }
+    return 0;
+}
+
+int prepare(B200Codec* h, const int32_t* seqlens, int n_utts, cudaStream_t s) {
+    B200_CHECK(h != nullptr, "null handle");
+    B200_CHECK(h->finalized, "decode called before b200codec_finalize_weights");
+    B200_CHECK(seqlens != nullptr, "null seqlens");
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    if (build_plan(h, seqlens, n_utts, kGap, s)) return 1;
+    if (ensure_workspace(h, h->rs.rows)) return 1;
+    return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* b200codec_last_error(void) { return g_err; }
+
+int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
+    g_err[0] = 0;
+    B200_CHECK(cfg != nullptr && out != nullptr, "b200codec_create: null argument");
+    B200_CHECK(cfg->abi_version == B200CODEC_ABI_VERSION, "ABI version mismatch: caller %d, library %d",
+               cfg->abi_version, B200CODEC_ABI_VERSION);
+    B200_CHECK(cfg->n_upsample == 0,
+               "upsample_factors are not supported yet: the 48 kHz UpSamplerBlock variant "
+               "(tts/core/codec/upsampler.py) is a NEXT row (SURVEY.md 8f-1)");
+    B200_CHECK(cfg->hop_length > 0 && cfg->sample_rate / cfg->hop_length == 50,
+               "Current hop length %d and upsample factors None do not match the target sample "
+               "rate %d.", cfg->hop_length, cfg->sample_rate);  // decoder.py:31-37
+    B200_CHECK(cfg->hop_length == 320, "only hop_length == 320 (xcodec2, 16 kHz) is instantiated");
+    B200_CHECK(cfg->precision == B200CODEC_BF16 || cfg->precision == B200CODEC_FP16,
+               "precision %d is not available (bf16 = 0, fp16 = 1)", cfg->precision);
+    B200_CHECK(cfg->hidden_dim == 1024 && cfg->heads == 16 && cfg->vq_dim == 2048 &&
+               cfg->depth >= 1 && cfg->depth <= 64,
+               "unsupported architecture (hidden %d heads %d vq %d depth %d)", cfg->hidden_dim,
+               cfg->heads, cfg->vq_dim, cfg->depth);
+    int ndev = 0;
+    B200_CUDA_OK(cudaGetDeviceCount(&ndev));
+    B200_CHECK(cfg->device >= 0 && cfg->device < ndev, "CUDA device %d not present (%d devices); "
+               "this library has no CPU fallback", cfg->device, ndev);
+    B200_CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    B200_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    B200_CHECK(prop.major == 10, "device %d is sm_%d%d; b200codec kernels are built for sm_100a only",
+               cfg->device, prop.major, prop.minor);
+
+    B200Codec* h = new B200Codec();
+    h->cfg = *cfg;
+    h->C = cfg->hidden_dim;
+    h->H = cfg->heads;
+    h->L = cfg->depth;
+    h->V = cfg->vq_dim;
+    h->hop = cfg->hop_length;
+    h->n_fft = 4 * cfg->hop_length;
+    h->n_bins = h->n_fft / 2 + 1;
+    build_specs(h);
+    h->master.assign(h->specs.size(), nullptr);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->err_flag_host), sizeof(int),
+                      cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->err_flag_dev), h->err_flag_host, 0) !=
+            cudaSuccess) {
+        set_error("cannot allocate the mapped error flag");
+        delete h;
+        return 1;
+    }
+    *h->err_flag_host = 0;
+    *out = h;
+    return 0;
+}
+
+void b200codec_destroy(B200Codec* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (float* p : h->master)
+        if (p) cudaFree(p);
+    h->wbuf.release();
+    h->ws.release();
+    h->plan_dev.release();
+    h->io_ids.release();
+    h->io_wav.release();
+    if (h->plan_host) cudaFreeHost(h->plan_host);
+    if (h->head_bias_pad) cudaFree(h->head_bias_pad);
+    if (h->twiddle) cudaFree(h->twiddle);
+    if (h->rope_cos) cudaFree(h->rope_cos);
+    if (h->rope_sin) cudaFree(h->rope_sin);
+    if (h->gn_stats) cudaFree(h->gn_stats);
+    if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+    delete h;
+}
+
+int b200codec_num_tensors(const B200Codec* h) { return h ? static_cast<int>(h->specs.size()) : 0; }
+
+const char* b200codec_tensor_key(const B200Codec* h, int i) {
+    if (!h || i < 0 || i >= static_cast<int>(h->specs.size())) return nullptr;
+    return h->specs[i].key.c_str();
+}
+
+int b200codec_tensor_shape(const B200Codec* h, int i, int64_t shape_out[4]) {
+    if (!h || i < 0 || i >= static_cast<int>(h->specs.size())) return -1;
+    const auto& s = h->specs[i].shape;
+    for (size_t d = 0; d < s.size() && d < 4; ++d) shape_out[d] = s[d];
+    return static_cast<int>(s.size());
+}
+
+int b200codec_load_tensor(B200Codec* h, const char* key, const void* host_ptr, int dtype,
+                          const int64_t* shape, int ndim) {
+    B200_CHECK(h && key && host_ptr && shape, "b200codec_load_tensor: null argument");
+    auto it = h->index.find(key);
+    B200_CHECK(it != h->index.end(), "Unexpected key(s) in state_dict: \"%s\"", key);
+    const TensorSpec& sp = h->specs[it->second];
+    bool ok = static_cast<int>(sp.shape.size()) == ndim;
+    for (int d = 0; ok && d < ndim; ++d) ok = sp.shape[d] == shape[d];
+    B200_CHECK(ok, "size mismatch for %s: checkpoint tensor does not match the model shape", key);
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    const size_t n = sp.numel();
+    std::vector<float> tmp;
+    const float* src = nullptr;
+    if (dtype == B200CODEC_F32) {
+        src = static_cast<const float*>(host_ptr);
+    } else {
+        tmp.resize(n);
+        if (dtype == B200CODEC_F64) {
+            const double* p = static_cast<const double*>(host_ptr);
+            for (size_t i = 0; i < n; ++i) tmp[i] = static_cast<float>(p[i]);
+        } else if (dtype == B200CODEC_F16) {
+            const __half* p = static_cast<const __half*>(host_ptr);
+            for (size_t i = 0; i < n; ++i) tmp[i] = __half2float(p[i]);
+        } else if (dtype == B200CODEC_BF16_T) {
+            const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(host_ptr);
+            for (size_t i = 0; i < n; ++i) tmp[i] = __bfloat162float(p[i]);
+        } else {
+            set_error("b200codec_load_tensor: unsupported dtype %d for %s", dtype, key);
+            return 1;
+        }
+        src = tmp.data();
+    }
+    float*& dst = h->master[it->second];
+    if (dst == nullptr) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dst), n * sizeof(float)));
+    B200_CUDA_OK(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    h->finalized = false;
+    return 0;
+}
+
+int b200codec_read_tensor(const B200Codec* h, const char* key, float* host_out, size_t n_elems) {
+    B200_CHECK(h && key && host_out, "b200codec_read_tensor: null argument");
+    auto it = h->index.find(key);
+    B200_CHECK(it != h->index.end(), "unknown tensor \"%s\"", key);
+    const TensorSpec& sp = h->specs[it->second];
+    B200_CHECK(sp.numel() == n_elems, "read_tensor %s: expected %zu elements, got %zu", key,
+               sp.numel(), n_elems);
+    B200_CHECK(h->master[it->second] != nullptr, "tensor \"%s\" has not been loaded", key);
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    B200_CUDA_OK(cudaMemcpy(host_out, h->master[it->second], n_elems * sizeof(float),
+                            cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200codec_finalize_weights(B200Codec* h, void* stream) {
+    B200_CHECK(h != nullptr, "null handle");
+    if (h->finalized) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    std::string missing;
+    for (size_t i = 0; i < h->specs.size(); ++i)
+        if (h->master[i] == nullptr) {
+            if (missing.size() < 600) missing += (missing.empty() ? "\"" : ", \"") + h->specs[i].key + "\"";
+        }
+    B200_CHECK(missing.empty(), "Missing key(s) in state_dict: %s", missing.c_str());
+
+    const int C = h->C, V = h->V, L = h->L, prec = h->cfg.precision;
+    const size_t es = operand_bytes(prec);
+    const size_t n_head = static_cast<size_t>(h->n_fft + 2) * C;
+    size_t elems = static_cast<size_t>(C) * V + static_cast<size_t>(C) * C * 7 +
+                   8 * static_cast<size_t>(C) * C * 3 +
+                   static_cast<size_t>(L) * (3ull * C * C + 1ull * C * C + 8ull * C * C) + n_head;
+    if (h->wbuf.ensure(elems * es + 64 * 1024)) return 1;
+    uint8_t* wp = h->wbuf.as<uint8_t>();
+    auto take = [&](size_t n) {
+        void* r = wp;
+        wp += (n * es + 255) & ~static_cast<size_t>(255);
+        return r;
+    };
+    // RoPE tables: torchtune.modules.RotaryPositionalEmbeddings(dim=64, base=10000) evaluated
+    // at "position" = head index (decoder_modules.py:276-281 passes [b, h, t, d]).
+    {
+        const int half = 32;
+        std::vector<float> c(h->H * half), sn(h->H * half);
+        for (int hd = 0; hd < h->H; ++hd)
+            for (int j = 0; j < half; ++j) {
+                const float theta = 1.0f / powf(10000.0f, static_cast<float>(2 * j) / 64.0f);
+                const float ang = static_cast<float>(hd) * theta;
+                c[hd * half + j] = cosf(ang);
+                sn[hd * half + j] = sinf(ang);
+            }
+        if (!h->rope_cos) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->rope_cos), c.size() * 4));
+        if (!h->rope_sin) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->rope_sin), c.size() * 4));
+        B200_CUDA_OK(cudaMemcpy(h->rope_cos, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+        B200_CUDA_OK(cudaMemcpy(h->rope_sin, sn.data(), c.size() * 4, cudaMemcpyHostToDevice));
+    }
+    float* scratch = nullptr;
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&scratch), 3ull * C * C * sizeof(float)));
+
+    h->w_fc = take(static_cast<size_t>(C) * V);
+    if (launch_repack_weight(prec, h->m("fc_post_a.weight"), h->w_fc, C, V, 1, s)) return 1;
+    h->w_embed = take(static_cast<size_t>(C) * C * 7);
+    if (launch_repack_weight(prec, h->m("decoder.backbone.embed.weight"), h->w_embed, C, C, 7, s)) return 1;
+    const char* nets[4] = {"decoder.backbone.prior_net.0.", "decoder.backbone.prior_net.1.",
+                           "decoder.backbone.post_net.0.", "decoder.backbone.post_net.1."};
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = nets[i];
+        ResBlockW& r = h->res[i];
+        r.gn1_w = h->m(p + "norm1.weight");
+        r.gn1_b = h->m(p + "norm1.bias");
+        r.b1 = h->m(p + "conv1.bias");
+        r.gn2_w = h->m(p + "norm2.weight");
+        r.gn2_b = h->m(p + "norm2.bias");
+        r.b2 = h->m(p + "conv2.bias");
+        r.w1 = take(static_cast<size_t>(C) * C * 3);
+        r.w2 = take(static_cast<size_t>(C) * C * 3);
+        if (launch_repack_weight(prec, h->m(p + "conv1.weight"), r.w1, C, C, 3, s)) return 1;
+        if (launch_repack_weight(prec, h->m(p + "conv2.weight"), r.w2, C, C, 3, s)) return 1;
+    }
+    for (int l = 0; l < L; ++l) {
+        const std::string p = "decoder.backbone.transformers." + std::to_string(l) + ".";
+        LayerW& w = h->layers[l];
+        w.att_norm = h->m(p + "att_norm.weight");
+        w.ffn_norm = h->m(p + "ffn_norm.weight");
+        w.qkv = take(3ull * C * C);
+        w.proj = take(1ull * C * C);
+        w.fc1 = take(4ull * C * C);
+        w.fc2 = take(4ull * C * C);
+        // fold the head-indexed rotary embedding into the q and k rows of c_attn (fp32), then cast
+        B200_CUDA_OK(cudaMemcpyAsync(scratch, h->m(p + "att.c_attn.weight"), 3ull * C * C * 4,
+                                     cudaMemcpyDeviceToDevice, s));
+        if (launch_fold_rope(scratch, h->H, C / h->H, C, h->rope_cos, h->rope_sin, s)) return 1;
+        if (launch_repack_weight(prec, scratch, w.qkv, 3 * C, C, 1, s)) return 1;
+        if (launch_repack_weight(prec, h->m(p + "att.c_proj.weight"), w.proj, C, C, 1, s)) return 1;
+        if (launch_repack_weight(prec, h->m(p + "mlp.fc1.weight"), w.fc1, 4 * C, C, 1, s)) return 1;
+        if (launch_repack_weight(prec, h->m(p + "mlp.fc2.weight"), w.fc2, C, 4 * C, 1, s)) return 1;
+    }
+    h->w_head = take(n_head);
+    if (launch_repack_weight(prec, h->m("decoder.head.out.weight"), h->w_head, h->n_fft + 2, C, 1, s)) return 1;
+    if (!h->head_bias_pad)
+        B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->head_bias_pad), kHeadLd * sizeof(float)));
+    B200_CUDA_OK(cudaMemsetAsync(h->head_bias_pad, 0, kHeadLd * sizeof(float), s));
+    B200_CUDA_OK(cudaMemcpyAsync(h->head_bias_pad, h->m("decoder.head.out.bias"),
+                                 (h->n_fft + 2) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    {
+        std::vector<float2> tw(h->n_fft);
+        for (int i = 0; i < h->n_fft; ++i) {
+            const double a = 2.0 * M_PI * i / h->n_fft;
+            tw[i] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+        }
+        if (!h->twiddle) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->twiddle), tw.size() * sizeof(float2)));
+        B200_CUDA_OK(cudaMemcpy(h->twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    B200_CUDA_OK(cudaFree(scratch));
+    h->finalized = true;
+    return 0;
+}
+
+int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
+                            const int32_t* seqlens_host, int n_utts, float* wav_dev, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (prepare(h, seqlens_host, n_utts, s)) return 1;
+    B200_CHECK(ids_dev && wav_dev, "decode: null device buffer");
+    // 8 GroupNorm layers x [n_utts][32 groups][sum, sumsq] fp64
+    const size_t need = sizeof(double) * 8 * static_cast<size_t>(n_utts) * 64;
+    if (h->gn_stats_bytes < need) {
+        if (h->gn_stats) B200_CUDA_OK(cudaFree(h->gn_stats));
+        h->gn_stats = nullptr;
+        h->gn_stats_bytes = 0;
+        B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->gn_stats), need * 2));
+        h->gn_stats_bytes = need * 2;
+    }
+    const int rc = forward(h, ids_dev, id_type, wav_dev, s);
+    if (h->profiling) {
+        cudaStreamSynchronize(s);
+        collect_timers(h);
+    }
+    return rc;
+}
+
+int b200codec_take_id_error(B200Codec* h) {
+    if (!h || !h->err_flag_host) return 0;
+    const int v = *reinterpret_cast<volatile int*>(h->err_flag_host);
+    *reinterpret_cast<volatile int*>(h->err_flag_host) = 0;
+    return v;
+}
+
+int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
+                          const int32_t* seqlens_host, int n_utts, float* wav_host, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CHECK(h && ids_host && wav_host && seqlens_host, "decode_host: null argument");
+    B200_CHECK(n_utts > 0, "decode: empty batch (no utterances)");
+    int64_t toks = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        B200_CHECK(seqlens_host[u] > 0, "decode: utterance %d is empty", u);
+        toks += seqlens_host[u];
+    }
+    if (check_ids_host(ids_host, id_type, toks)) return 1;
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    const size_t id_bytes = static_cast<size_t>(toks) * (id_type == B200CODEC_IDS_I64 ? 8 : 4);
+    const size_t wav_bytes = static_cast<size_t>(toks) * h->hop * sizeof(float);
+    if (h->io_ids.ensure(id_bytes)) return 1;
+    if (h->io_wav.ensure(wav_bytes)) return 1;
+    B200_CUDA_OK(cudaMemcpyAsync(h->io_ids.p, ids_host, id_bytes, cudaMemcpyHostToDevice, s));
+    if (b200codec_decode_varlen(h, h->io_ids.p, id_type, seqlens_host, n_utts, h->io_wav.as<float>(), s))
+        return 1;
+    B200_CUDA_OK(cudaMemcpyAsync(wav_host, h->io_wav.p, wav_bytes, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0; }
+
+int b200codec_profile(B200Codec* h, int on) {
+    B200_CHECK(h != nullptr, "null handle");
+    h->profiling = on != 0;
+    h->stage_ms.clear();
+    h->stage_order.clear();
+    return 0;
+}
+
+int b200codec_stage_times(B200Codec* h, int max_stages, const char** names_out, float* ms_out,
+                          int* n_out) {
+    B200_CHECK(h && names_out && ms_out && n_out, "stage_times: null argument");
+    int n = 0;
+    for (const auto& name : h->stage_order) {
+        if (n >= max_stages) break;
+        names_out[n] = name.c_str();
+        ms_out[n] = h->stage_ms[name];
+        ++n;
+    }
+    *n_out = n;
+    return 0;
+}
+
+// ---- per-stage entry points -------------------------------------------------------------
+
+int b200codec_fsq_lookup(B200Codec* h, const void* ids_dev, int id_type, int64_t n, float* out_dev,
+                         void* stream) {
+    B200_CHECK(h && ids_dev && out_dev, "fsq_lookup: null argument");
+    const float* w = h->m("decoder.quantizer.project_out.weight");
+    const float* b = h->m("decoder.quantizer.project_out.bias");
+    B200_CHECK(w && b, "fsq_lookup: quantizer.project_out has not been loaded");
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    if (launch_fsq_lookup(ids_dev, id_type, nullptr, static_cast<int>(n), w, b, h->V, out_dev, h->V,
+                          -1, h->err_flag_dev, static_cast<cudaStream_t>(stream)))
+        return 1;
+    h->launches++;
+    return 0;
+}
+
+int b200codec_istft(B200Codec* h, const float* x_pred_dev, int ld, const int32_t* seqlens_host,
+                    int n_utts, float* wav_dev, void* stream) {
+    B200_CHECK(h && x_pred_dev && wav_dev && seqlens_host, "istft: null argument");
+    B200_CHECK(h->finalized, "istft called before b200codec_finalize_weights");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    TempPlan tp;
+    if (tp.build(seqlens_host, n_utts, s)) return 1;
+    IstftTables tab;
+    tab.twiddle = h->twiddle;
+    tab.window = h->m("decoder.head.istft.window");
+    if (launch_istft(x_pred_dev, ld, tp.rs, tab, h->hop, wav_dev, s)) return 1;
+    h->launches++;
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int b200codec_gemm(int precision, const void* a_dev, const void* w_dev, int M, int N, int Cin,
+                   int taps, void* out_dev, int out_dtype, int ldc, const float* bias_dev,
+                   const float* residual_dev, int ld_res, int act, void* stream) {
+    B200_CHECK(a_dev && w_dev && out_dev, "gemm: null argument");
+    GemmCall c;
+    c.precision = precision;
+    c.a = a_dev;
+    c.a_rows = M;
+    c.Cin = Cin;
+    c.w = w_dev;
+    c.N = N;
+    c.taps = taps;
+    c.out = out_dev;
+    c.out_fp32 = out_dtype == 0 ? 1 : 0;
+    c.ldc = ldc;
+    c.n_store = (N + 31) / 32 * 32;
+    c.bias = bias_dev;
+    c.residual = residual_dev;
+    c.ld_res = ld_res;
+    c.row_valid = nullptr;
+    c.act = act;
+    c.row_sumsq = nullptr;
+    B200_CHECK(c.n_store <= ldc, "gemm: ldc (%d) must cover N rounded up to 32 (%d)", ldc, c.n_store);
+    return launch_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+int b200codec_rmsnorm(int precision, const float* x_dev, const float* w_dev, int rows, int dim,
+                      float eps, void* out_dev, void* stream) {
+    B200_CHECK(x_dev && w_dev && out_dev, "rmsnorm: null argument");
+    return launch_rmsnorm(precision, x_dev, w_dev, rows, dim, eps, out_dev,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int b200codec_layernorm(int precision, const float* x_dev, const float* w_dev, const float* b_dev,
+                        int rows, int dim, float eps, void* out_dev, void* stream) {
+    B200_CHECK(x_dev && w_dev && b_dev && out_dev, "layernorm: null argument");
+    return launch_layernorm(precision, x_dev, w_dev, b_dev, rows, dim, eps, out_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int b200codec_groupnorm_swish(int precision, const float* x_dev, const float* gamma_dev,
+                              const float* beta_dev, const int32_t* seqlens_host, int n_utts,
+                              int dim, float eps, void* out_dev, void* stream) {
+    B200_CHECK(x_dev && gamma_dev && beta_dev && out_dev && seqlens_host, "groupnorm: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TempPlan tp;
+    if (tp.build(seqlens_host, n_utts, s)) return 1;
+    double* stats = nullptr;
+    const size_t bytes = sizeof(double) * 64 * static_cast<size_t>(n_utts);
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stats), bytes));
+    int rc = 0;
+    if (cudaMemsetAsync(stats, 0, bytes, s) != cudaSuccess) rc = 1;
+    if (!rc) rc = launch_groupnorm_stats(x_dev, tp.rs, dim, stats, s);
+    if (!rc) rc = launch_groupnorm_apply_swish(precision, x_dev, tp.rs, dim, stats, gamma_dev,
+                                               beta_dev, eps, out_dev, s);
+    cudaStreamSynchronize(s);
+    cudaFree(stats);
+    return rc;
+}
+
+int b200codec_attention(int precision, const void* qkv_dev, const int32_t* seqlens_host, int n_utts,
+                        int heads, void* out_dev, void* stream) {
+    B200_CHECK(qkv_dev && out_dev && seqlens_host, "attention: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TempPlan tp;
+    if (tp.build(seqlens_host, n_utts, s)) return 1;
+    int rc = launch_attention(precision, qkv_dev, tp.rs, heads, out_dev, s);
+    cudaStreamSynchronize(s);
+    return rc;
+}
+
+}  // extern "C"

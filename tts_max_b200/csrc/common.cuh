@@ -1,0 +1,305 @@
+// Shared device/host helpers for the B200 (sm_100a) codec-decode kernels.
+//
+// Everything here is hand-written PTX glue for the Blackwell execution model:
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM alloc / ld / commit).
+// No CUTLASS types are used; descriptor encodings follow the PTX ISA tables
+// ("tcgen05 shared memory descriptor", "instruction descriptor, kind::f16").
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+// error plumbing (C-ABI never aborts; see codec.cu::set_error)
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define B200_CUDA_OK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ::b200::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,      \
+                              cudaGetErrorString(_e));                                  \
+            return 1;                                                                   \
+        }                                                                               \
+    } while (0)
+
+#define B200_CHECK(cond, ...)                                                           \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            ::b200::set_error(__VA_ARGS__);                                             \
+            return 1;                                                                   \
+        }                                                                               \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+// ---------------------------------------------------------------------------
+// small device utilities
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// 16-bit storage type helpers: the GEMM operand type is bf16 or fp16
+// (both run on tcgen05 kind::f16 at the same rate).
+template <typename T>
+struct Half16;
+template <>
+struct Half16<__nv_bfloat16> {
+    using T2 = __nv_bfloat162;
+    static constexpr uint32_t kUmmaFormat = 1;  // BF16
+    __device__ static __forceinline__ uint32_t pack(float a, float b) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ static __forceinline__ float2 unpack(uint32_t u) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    }
+    __host__ __device__ static __forceinline__ __nv_bfloat16 from_float(float f) {
+        return __float2bfloat16_rn(f);
+    }
+};
+template <>
+struct Half16<__half> {
+    using T2 = __half2;
+    static constexpr uint32_t kUmmaFormat = 0;  // F16
+    __device__ static __forceinline__ uint32_t pack(float a, float b) {
+        // saturate instead of overflowing to inf
+        a = fminf(fmaxf(a, -65504.f), 65504.f);
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ static __forceinline__ float2 unpack(uint32_t u) {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    }
+    __host__ __device__ static __forceinline__ __half from_float(float f) {
+        f = f < -65504.f ? -65504.f : (f > 65504.f ? 65504.f : f);
+        return __float2half_rn(f);
+    }
+};
+
+// tcgen05 instruction-descriptor operand format codes (kind::f16 / kind::tf32)
+template <typename T>
+struct UmmaFmt;
+template <>
+struct UmmaFmt<__half> {
+    static constexpr uint32_t value = 0;
+};
+template <>
+struct UmmaFmt<__nv_bfloat16> {
+    static constexpr uint32_t value = 1;
+};
+template <>
+struct UmmaFmt<float> {
+    static constexpr uint32_t value = 2;
+};
+
+// ---------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Bounded spin: a protocol bug must surface as a trap (-> CUDA error -> Python
+// exception), never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("b200codec: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+// 2-D tiled load global -> shared (this CTA), completion on `bar` (complete_tx).
+// c0 = innermost (contiguous) coordinate, c1 = row coordinate. Out-of-bounds
+// parts of the box (including negative coordinates) are zero-filled.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tc05_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc05_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// one full warp; writes the TMEM base address into *dst_smem
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    static_assert(kCols >= 32 && kCols <= 512 && (kCols & (kCols - 1)) == 0, "bad TMEM cols");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+                 : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers bf16 and fp16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// kind::tf32 : fp32 storage in smem, 10-bit mantissa multiply, fp32 accumulate.
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
+                     "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major operand tile stored as rows of
+// exactly 128 bytes with the 128-byte swizzle (what TMA SWIZZLE_128B writes):
+//   bits [0,14)  start address >> 4
+//   bits [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
+//   bits [32,46) stride byte offset >> 4  (8 rows * 128 B = 1024 B -> 64)
+//   bits [46,48) descriptor version = 1 (Blackwell)
+//   bits [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// Instruction descriptor (kind::f16 / kind::tf32), K-major A and B, fp32 accumulate:
+//   [4,6) D format (1 = f32)   [7,10) A format   [10,13) B format
+//   [15] A major (0 = K)       [16] B major (0 = K)
+//   [17,23) N >> 3             [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t ab_format, uint32_t M, uint32_t N) {
+    return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
+}
+
+}  // namespace b200

@@ -1,0 +1,180 @@
+// Host side of the tcgen05 GEMM: TMA descriptor encoding, dispatch, weight repacking.
+#include "gemm_tc05.cuh"
+
+#include <cudaTypedefs.h>
+
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+// cuTensorMapEncodeTiled is a driver API; fetch it through the runtime so the library has
+// no link-time dependency on libcuda (it must load on a CPU-only box for the symbol tests).
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+template <typename T>
+__global__ void repack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int N,
+                                     int Cin, int taps) {
+    // dst[n, tap*Cin + c] = src[n, c, tap]
+    const size_t total = static_cast<size_t>(N) * Cin * taps;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cin);
+        const size_t rest = i / Cin;
+        const int tap = static_cast<int>(rest % taps);
+        const size_t n = rest / taps;
+        const float v = src[(n * Cin + c) * taps + tap];
+        dst[i] = Half16<T>::from_float(v);
+    }
+}
+
+__global__ void fold_rope_kernel(float* __restrict__ w, int heads, int head_dim, int K,
+                                 const float* __restrict__ cos_tab,
+                                 const float* __restrict__ sin_tab) {
+    // rows: r in {q, k}, head h, pair j -> rows (2j, 2j+1); angle index [h, j]
+    const int half = head_dim / 2;
+    const int pairs = 2 * heads * half;
+    for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+        const int j = pr % half;
+        const int h = (pr / half) % heads;
+        const int r = pr / (half * heads);
+        const float c = cos_tab[h * half + j], s = sin_tab[h * half + j];
+        float* row0 = w + static_cast<size_t>((r * heads + h) * head_dim + 2 * j) * K;
+        float* row1 = row0 + K;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float a = row0[k], b = row1[k];
+            row0[k] = a * c - b * s;  // torchtune: x0*cos - x1*sin
+            row1[k] = b * c + a * s;  //            x1*cos + x0*sin
+        }
+    }
+}
+
+template <typename InT>
+int dispatch(const GemmCall& c, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+             bool wide, cudaStream_t stream) {
+    if (c.out_fp32) {
+        if (wide) return launch_gemm_tc05<256, InT, float, 4>(ta, tb, p, stream);
+        return launch_gemm_tc05<128, InT, float, 6>(ta, tb, p, stream);
+    }
+    if (wide) return launch_gemm_tc05<256, InT, InT, 4>(ta, tb, p, stream);
+    return launch_gemm_tc05<128, InT, InT, 6>(ta, tb, p, stream);
+}
+
+}  // namespace
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_rows) {
+    auto fn = get_encode_fn();
+    B200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    CUtensorMapDataType dt;
+    uint64_t esz;
+    switch (dtype) {
+        case kTmapBf16: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; esz = 2; break;
+        case kTmapF16: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; esz = 2; break;
+        case kTmapF32: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; esz = 4; break;
+        default: set_error("make_tmap_2d: bad dtype %d", dtype); return 1;
+    }
+    B200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    B200_CHECK((ld_elems * esz) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+    B200_CHECK(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static bool gemm_is_wide(const GemmCall& c) {
+    return c.n_store >= 1024 && (c.n_store % 256 == 0);
+}
+
+int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out) {
+    const int dt = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
+    if (tmap_a_out != nullptr &&
+        make_tmap_2d(static_cast<CUtensorMap*>(tmap_a_out), c.a, dt, c.a_rows, c.Cin, c.Cin,
+                     kGemmBlockM))
+        return 1;
+    if (tmap_b_out != nullptr &&
+        make_tmap_2d(static_cast<CUtensorMap*>(tmap_b_out), c.w, dt, c.N,
+                     static_cast<uint64_t>(c.taps) * c.Cin, static_cast<uint64_t>(c.taps) * c.Cin,
+                     gemm_is_wide(c) ? 256 : 128))
+        return 1;
+    return 0;
+}
+
+int launch_gemm(const GemmCall& c, cudaStream_t stream) {
+    B200_CHECK(c.precision == kPrecBf16 || c.precision == kPrecFp16,
+               "gemm: unsupported precision %d", c.precision);
+    const int block_k = 64;
+    B200_CHECK(c.Cin % block_k == 0, "gemm: Cin (%d) must be a multiple of %d", c.Cin, block_k);
+    B200_CHECK(c.n_store % 32 == 0 && c.n_store <= c.ldc, "gemm: bad n_store %d (ldc %d)",
+               c.n_store, c.ldc);
+    B200_CHECK(c.taps >= 1 && c.taps % 2 == 1, "gemm: taps must be odd");
+    if (c.a_rows <= 0) return 0;
+    const bool wide = gemm_is_wide(c);
+    alignas(64) CUtensorMap ta, tb;
+    if (c.tmap_a != nullptr) ta = *static_cast<const CUtensorMap*>(c.tmap_a);
+    if (c.tmap_b != nullptr) tb = *static_cast<const CUtensorMap*>(c.tmap_b);
+    if (encode_gemm_tmaps(c, c.tmap_a ? nullptr : &ta, c.tmap_b ? nullptr : &tb)) return 1;
+    GemmParams p;
+    p.M = c.a_rows;
+    p.n_store = c.n_store;
+    p.k_blocks_per_tap = c.Cin / block_k;
+    p.taps = c.taps;
+    p.tap_pad = c.taps / 2;
+    p.out = c.out;
+    p.ldc = c.ldc;
+    p.bias = c.bias;
+    p.residual = c.residual;
+    p.ld_res = c.ld_res;
+    p.row_valid = c.row_valid;
+    p.act = c.act;
+    p.row_sumsq = c.row_sumsq;
+    if (c.precision == kPrecBf16) return dispatch<__nv_bfloat16>(c, ta, tb, p, wide, stream);
+    return dispatch<__half>(c, ta, tb, p, wide, stream);
+}
+
+int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,
+                         cudaStream_t stream) {
+    const size_t total = static_cast<size_t>(N) * Cin * taps;
+    if (total == 0) return 0;
+    const int grid = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    if (prec == kPrecBf16)
+        repack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+            src, static_cast<__nv_bfloat16*>(dst), N, Cin, taps);
+    else if (prec == kPrecFp16)
+        repack_weight_kernel<__half><<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), N,
+                                                               Cin, taps);
+    else {
+        set_error("repack: unsupported precision %d", prec);
+        return 1;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_fold_rope(float* w_qkv, int heads, int head_dim, int K, const float* cos_tab,
+                     const float* sin_tab, cudaStream_t stream) {
+    const int pairs = 2 * heads * (head_dim / 2);
+    fold_rope_kernel<<<pairs, 256, 0, stream>>>(w_qkv, heads, head_dim, K, cos_tab, sin_tab);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200

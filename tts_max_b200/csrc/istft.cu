@@ -1,0 +1,219 @@
+// K13 + K14: complex spectrum + inverse STFT ("same" padding) as one shared-memory-staged kernel.
+//
+// Replaces (reference):
+//   ISTFTHead.forward after self.out   tts/core/codec/decoder_modules.py:131-148
+//       mag = clip(exp(m), max=100); S = mag * (cos p + i sin p)
+//   ISTFT.forward, padding == "same"   tts/core/codec/decoder_modules.py:59-93
+//       irfft(S, n_fft, norm="backward") * hann -> overlap-add (fold) -> trim (win-hop)/2
+//       -> divide by the overlap-added squared window
+//
+// Input is the head Linear output, token-major [rows, ld] fp32: columns [0, n_bins) are the
+// log-magnitudes and [n_bins, 2*n_bins) the phases of one frame (that is what
+// transpose(1,2).chunk(2, dim=1) selects). n_fft = 4 * hop = 1280, n_bins = 641.
+//
+// One CTA produces kIstftOutHops * hop consecutive output samples of one utterance. Output hop b
+// receives frames b-2 .. b+2, so the CTA transforms kIstftOutHops + 4 frames (in groups of 4)
+// and overlap-adds them in shared memory; nothing but the finished samples goes back to HBM.
+// The length-1280 real inverse FFT is a length-640 complex inverse FFT of the packed
+// even/odd spectrum (Stockham autosort, radix 4-4-4-10) -- irfft ignores Im(S[0]) and
+// Im(S[n_fft/2]), and so does the packing below.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kHop = 320;
+constexpr int kNfft = 1280;
+constexpr int kHalf = 640;   // complex FFT length
+constexpr int kBins = 641;
+constexpr int kGroup = 4;    // frames transformed together
+constexpr int kIstftThreads = 256;
+constexpr int kTileFrames = kIstftOutHops + 4;
+static_assert(kTileFrames % kGroup == 0, "tile frames must be a multiple of the group");
+
+struct IstftSmem {
+    float2 buf_a[kGroup][kHalf];
+    float2 buf_b[kGroup][kHalf];
+    float2 tw[kNfft];
+    float win[kNfft];
+    float ola[kIstftOutHops * kHop];
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// one Stockham pass of radix R over `kGroup` independent length-640 transforms
+template <int R>
+__device__ __forceinline__ void stockham_pass(const float2 (*src)[kHalf], float2 (*dst)[kHalf],
+                                              const float2* tw, int Ns) {
+    constexpr int kButterflies = kHalf / R;
+    const int tw_stride = kNfft / (Ns * R);
+    for (int idx = threadIdx.x; idx < kGroup * kButterflies; idx += kIstftThreads) {
+        const int f = idx / kButterflies;
+        const int j = idx - f * kButterflies;
+        const int k = j % Ns;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = src[f][j + r * kButterflies];
+            if (r > 0) v[r] = cmul(v[r], tw[r * k * tw_stride]);
+        }
+        const int j0 = (j / Ns) * Ns * R + k;
+        if constexpr (R == 4) {
+            // inverse DFT-4: out[q] = sum_r v[r] * (+i)^(q r)
+            const float2 t0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
+            const float2 t1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+            const float2 t2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
+            const float2 d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+            const float2 t3 = make_float2(-d.y, d.x);  // i * d
+            dst[f][j0 + 0 * Ns] = make_float2(t0.x + t2.x, t0.y + t2.y);
+            dst[f][j0 + 1 * Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
+            dst[f][j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
+            dst[f][j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+        } else {
+            // direct inverse DFT-R with table twiddles exp(+2 pi i q r / R)
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                float2 acc = v[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    const float2 w = tw[((q * r) % R) * (kNfft / R)];
+                    acc.x += v[r].x * w.x - v[r].y * w.y;
+                    acc.y += v[r].x * w.y + v[r].y * w.x;
+                }
+                dst[f][j0 + q * Ns] = acc;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kIstftThreads)
+istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ work,
+             const int32_t* __restrict__ utt_row0, const int32_t* __restrict__ utt_len,
+             const int32_t* __restrict__ utt_tok0, const float2* __restrict__ twiddle,
+             const float* __restrict__ window, float* __restrict__ wav) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
+
+    const int4 wk = work[blockIdx.x];
+    const int utt = wk.x, b0 = wk.y;
+    const int T = utt_len[utt];
+    const int row0 = utt_row0[utt];
+    float* wav_u = wav + static_cast<size_t>(utt_tok0[utt]) * kHop;
+
+    for (int i = threadIdx.x; i < kNfft; i += kIstftThreads) {
+        sm.tw[i] = twiddle[i];
+        sm.win[i] = window[i];
+    }
+    for (int i = threadIdx.x; i < kIstftOutHops * kHop; i += kIstftThreads) sm.ola[i] = 0.f;
+    __syncthreads();
+
+    for (int g = 0; g < kTileFrames / kGroup; ++g) {
+        const int t_first = b0 - 2 + g * kGroup;  // absolute frame index of group slot 0
+        if (t_first >= T || t_first + kGroup <= 0) continue;  // uniform: whole group outside
+
+        // 1. spectrum: X[k] = min(exp(m_k), 100) * (cos p_k, sin p_k); Re X[640] parked in X[0].y
+        for (int idx = threadIdx.x; idx < kGroup * kBins; idx += kIstftThreads) {
+            const int f = idx / kBins;
+            const int k = idx - f * kBins;
+            const int t = t_first + f;
+            float2 X = make_float2(0.f, 0.f);
+            if (t >= 0 && t < T) {
+                const float* row = x_pred + static_cast<size_t>(row0 + t) * ld;
+                const float mag = fminf(expf(row[k]), 100.f);
+                float sn, cs;
+                sincosf(row[kBins + k], &sn, &cs);
+                X = make_float2(mag * cs, mag * sn);
+            }
+            if (k == 0) sm.buf_b[f][0].x = X.x;            // Im X[0] ignored by irfft
+            else if (k == kHalf) sm.buf_b[f][0].y = X.x;   // Im X[640] ignored by irfft
+            else sm.buf_b[f][k] = X;
+        }
+        __syncthreads();
+
+        // 2. pack: Z[k] = (X[k] + conj X[640-k]) + i * (X[k] - conj X[640-k]) * exp(+2 pi i k / 1280)
+        for (int idx = threadIdx.x; idx < kGroup * kHalf; idx += kIstftThreads) {
+            const int f = idx / kHalf;
+            const int k = idx - f * kHalf;
+            float2 xk, xr;
+            if (k == 0) {
+                xk = make_float2(sm.buf_b[f][0].x, 0.f);
+                xr = make_float2(sm.buf_b[f][0].y, 0.f);
+            } else {
+                xk = sm.buf_b[f][k];
+                const float2 m = sm.buf_b[f][kHalf - k];
+                xr = make_float2(m.x, -m.y);
+            }
+            const float2 e = make_float2(xk.x + xr.x, xk.y + xr.y);
+            const float2 o = cmul(make_float2(xk.x - xr.x, xk.y - xr.y), sm.tw[k]);
+            sm.buf_a[f][k] = make_float2(e.x - o.y, e.y + o.x);
+        }
+        __syncthreads();
+
+        // 3. length-640 inverse complex FFT, radix 4-4-4-10, ping-pong a -> b -> a -> b -> a
+        stockham_pass<4>(sm.buf_a, sm.buf_b, sm.tw, 1);
+        __syncthreads();
+        stockham_pass<4>(sm.buf_b, sm.buf_a, sm.tw, 4);
+        __syncthreads();
+        stockham_pass<4>(sm.buf_a, sm.buf_b, sm.tw, 16);
+        __syncthreads();
+        stockham_pass<10>(sm.buf_b, sm.buf_a, sm.tw, 64);
+        __syncthreads();
+
+        // 4. window, 1/n_fft and overlap-add (gather form: one thread per output sample).
+        //    buf_a[f] viewed as 1280 floats is the time-domain frame: x[2n] = Re z[n], x[2n+1] = Im z[n].
+        for (int n = threadIdx.x; n < kIstftOutHops * kHop; n += kIstftThreads) {
+            float acc = sm.ola[n];
+#pragma unroll
+            for (int f = 0; f < kGroup; ++f) {
+                const int t = t_first + f;
+                // frame t covers output samples [320 t - 480, 320 t + 800); n is relative to 320 b0
+                const int m = n + 480 - kHop * (t - b0);
+                if (t >= 0 && t < T && m >= 0 && m < kNfft)
+                    acc += reinterpret_cast<const float*>(sm.buf_a[f])[m] * (1.f / kNfft) * sm.win[m];
+            }
+            sm.ola[n] = acc;
+        }
+        __syncthreads();
+    }
+
+    // 5. normalise by the overlap-added squared window (edges see fewer frames) and store
+    const int n_out = min(kIstftOutHops, T - b0) * kHop;
+    for (int n = threadIdx.x; n < n_out; n += kIstftThreads) {
+        const int b = b0 + n / kHop;
+        float env = 0.f;
+#pragma unroll
+        for (int dt = -2; dt <= 2; ++dt) {
+            const int t = b + dt;
+            const int m = n + 480 - kHop * (t - b0);
+            if (t >= 0 && t < T && m >= 0 && m < kNfft) env = fmaf(sm.win[m], sm.win[m], env);
+        }
+        wav_u[static_cast<size_t>(b0) * kHop + n] = sm.ola[n] / env;
+    }
+}
+
+}  // namespace
+
+int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTables& tab, int hop,
+                 float* wav, cudaStream_t stream) {
+    B200_CHECK(hop == kHop, "istft: only hop_length == 320 (n_fft 1280) is instantiated (got %d)",
+               hop);
+    B200_CHECK(ld >= 2 * kBins, "istft: ld %d < %d", ld, 2 * kBins);
+    if (rs.n_istft_work <= 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(IstftSmem))));
+        configured = true;
+    }
+    istft_kernel<<<rs.n_istft_work, kIstftThreads, sizeof(IstftSmem), stream>>>(
+        x_pred, ld, rs.istft_work, rs.utt_row0, rs.utt_len, rs.utt_tok0, tab.twiddle, tab.window,
+        wav);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200

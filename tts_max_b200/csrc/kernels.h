@@ -1,0 +1,108 @@
+// Host-callable launchers of the sm_100a kernels (one .cu per family).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// precision codes == enum B200CodecPrecision
+constexpr int kPrecBf16 = 0;
+constexpr int kPrecFp16 = 1;
+constexpr int kPrecTf32 = 2;
+
+inline size_t operand_bytes(int precision) { return precision == kPrecTf32 ? 4 : 2; }
+
+// The padded row space all activations live in: utterance u occupies rows
+// [utt_row0[u], utt_row0[u] + utt_len[u]); `gap` rows that stay zero in every conv
+// operand separate consecutive utterances (conv halo). Device arrays.
+struct RowSpace {
+    int rows = 0;          // total padded rows R
+    int n_utts = 0;
+    int total_tokens = 0;  // sum(T)
+    int max_len = 0;
+    const int32_t* row_tok = nullptr;    // [R] packed token index, -1 on halo rows
+    const int32_t* row_utt = nullptr;    // [R] utterance index, -1 on halo rows
+    const uint8_t* row_valid = nullptr;  // [R] 1 on token rows
+    const int32_t* utt_row0 = nullptr;   // [n]
+    const int32_t* utt_len = nullptr;    // [n]
+    const int32_t* utt_tok0 = nullptr;   // [n] packed token offset (== sample offset / hop)
+    const int4* attn_work = nullptr;     // [n_attn_work] {row0, T, q0, 0}
+    int n_attn_work = 0;
+    const int4* istft_work = nullptr;    // [n_istft_work] {utt, b0, 0, 0}
+    int n_istft_work = 0;
+};
+
+constexpr int kAttnBlockQ = 64;     // query rows per attention CTA
+constexpr int kIstftOutHops = 12;   // output hops per ISTFT CTA (+4 halo frames)
+
+// ---- fsq.cu ----
+// out_prec: -1 -> fp32 output, else operand dtype of that precision.
+// row_tok == nullptr means rows are the packed tokens themselves.
+int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int rows,
+                      const float* w_out /*[C,8]*/, const float* b_out /*[C]*/, int channels,
+                      void* out, int ld, int out_prec, int* err_flag, cudaStream_t stream);
+
+// ---- norms.cu ----
+int launch_rmsnorm(int prec, const float* x, const float* w, int rows, int dim, float eps,
+                   void* out, cudaStream_t stream);
+int launch_layernorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
+                     float eps, void* out, cudaStream_t stream);
+// stats: double [n_utts][32][2] (sum, sumsq), must be zero on entry
+int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
+                           cudaStream_t stream);
+int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, int dim,
+                                 const double* stats, const float* gamma, const float* beta,
+                                 float eps, void* out, cudaStream_t stream);
+
+// ---- attention.cu ----
+int launch_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
+                     cudaStream_t stream);
+
+// ---- istft.cu ----
+struct IstftTables {
+    const float2* twiddle = nullptr;  // [n_fft] exp(+2*pi*i*m/n_fft)
+    const float* window = nullptr;    // [n_fft] from the checkpoint (decoder.head.istft.window)
+};
+int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTables& tab,
+                 int hop, float* wav, cudaStream_t stream);
+
+// ---- gemm_tc05.cu ----
+enum GemmAct : int { kActNone = 0, kActSilu = 1 };
+struct GemmCall {
+    int precision;       // operand dtype
+    const void* a;       // [a_rows, Cin]
+    int a_rows;
+    int Cin;
+    const void* w;       // [N, taps*Cin]
+    int N;               // logical out features (rows of w)
+    int taps;
+    void* out;
+    int out_fp32;        // 1 -> fp32 output, 0 -> operand dtype (tf32 mode: always fp32 storage)
+    int ldc;
+    int n_store;         // multiple of 32, <= ldc; columns >= N get bias only (zeros)
+    const float* bias;
+    const float* residual;
+    int ld_res;
+    const uint8_t* row_valid;
+    int act;
+    float* row_sumsq;
+    // optional pre-encoded TMA descriptors (CUtensorMap, 128 B each, 64-byte aligned);
+    // when null they are encoded on the fly.
+    const void* tmap_a = nullptr;
+    const void* tmap_b = nullptr;
+};
+constexpr size_t kTmapBytes = 128;
+int launch_gemm(const GemmCall& c, cudaStream_t stream);
+// encode the descriptors launch_gemm would build for `c` into tmap_a_out / tmap_b_out
+int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out);
+
+// ---- weight repack helpers (codec.cu uses them at finalize) ----
+// dst[n, tap*Cin + c] = src[n, c, tap]  (src is torch Conv1d weight [Cout, Cin, taps]), cast
+int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,
+                         cudaStream_t stream);
+// in-place on fp32 c_attn weight [3*H*64, K]: rotate q,k row pairs by the head-indexed angle
+int launch_fold_rope(float* w_qkv, int heads, int head_dim, int K, const float* cos_tab,
+                     const float* sin_tab, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,243 @@
+// K5 / K11 / K4-norm: RMSNorm, LayerNorm and GroupNorm(32)+swish on token-major
+// activations [rows, dim] fp32 -> tensor-core operand dtype.
+//
+// Replaces (reference):
+//   RMSNorm.forward                tts/core/codec/decoder_modules.py:233-236
+//   final_layer_norm (LayerNorm)   tts/core/codec/decoder_modules.py:373,399
+//   Normalize (GroupNorm 32, eps 1e-6, affine) + nonlinearity (swish)
+//                                  tts/core/codec/decoder_modules.py:151-159, 204-205, 212-213
+//
+// All three are HBM/L2-bound (4 B in + 2 B out per element): one warp per row with
+// 128-bit loads and stores for the row norms; GroupNorm statistics span (32 channels x T)
+// per utterance, so it is two-phase: a partial-sum kernel with fp64 atomics per
+// (utterance, group), then an apply+swish kernel that also writes the zero halo rows the
+// following implicit-GEMM conv relies on.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kNormWarps = 8;
+
+template <typename OutT>
+__device__ __forceinline__ void store8_out(OutT* dst, const float* v) {
+    uint4 u;
+    u.x = Half16<OutT>::pack(v[0], v[1]);
+    u.y = Half16<OutT>::pack(v[2], v[3]);
+    u.z = Half16<OutT>::pack(v[4], v[5]);
+    u.w = Half16<OutT>::pack(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+
+// dim == kChunks * 256; lane owns elements [lane*8 + i*256, +8) for i < kChunks
+template <typename OutT, int kChunks, bool kLayerNorm>
+__global__ void __launch_bounds__(kNormWarps * 32)
+rownorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+               const float* __restrict__ b, int rows, float eps, OutT* __restrict__ out) {
+    constexpr int dim = kChunks * 256;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kNormWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + static_cast<size_t>(row) * dim;
+    float v[kChunks][8];
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+        const float4* p = reinterpret_cast<const float4*>(xr + i * 256 + lane * 8);
+        const float4 a = p[0], c = p[1];
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+        v[i][4] = c.x; v[i][5] = c.y; v[i][6] = c.z; v[i][7] = c.w;
+    }
+    float mean = 0.f;
+    if (kLayerNorm) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        mean = warp_sum(s) * (1.f / dim);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = v[i][j] - mean;
+            ss = fmaf(d, d, ss);
+        }
+    const float var = warp_sum(ss) * (1.f / dim);
+    const float rstd = rsqrtf(var + eps);
+    OutT* orow = out + static_cast<size_t>(row) * dim;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+        const int c0 = i * 256 + lane * 8;
+        const float4* wp = reinterpret_cast<const float4*>(w + c0);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float o[8];
+        if (kLayerNorm) {
+            const float4* bp = reinterpret_cast<const float4*>(b + c0);
+            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rstd * wv[j];
+        }
+        store8_out<OutT>(orow + c0, o);
+    }
+}
+
+template <bool kLayerNorm>
+int launch_rownorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
+                   float eps, void* out, cudaStream_t stream) {
+    B200_CHECK(dim == 1024, "row norm: only dim == 1024 is instantiated (got %d)", dim);
+    if (rows <= 0) return 0;
+    const int grid = (rows + kNormWarps - 1) / kNormWarps;
+    if (prec == kPrecBf16)
+        rownorm_kernel<__nv_bfloat16, 4, kLayerNorm><<<grid, kNormWarps * 32, 0, stream>>>(
+            x, w, b, rows, eps, static_cast<__nv_bfloat16*>(out));
+    else if (prec == kPrecFp16)
+        rownorm_kernel<__half, 4, kLayerNorm><<<grid, kNormWarps * 32, 0, stream>>>(
+            x, w, b, rows, eps, static_cast<__half*>(out));
+    else {
+        set_error("row norm: unsupported precision %d", prec);
+        return 1;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// GroupNorm: 32 groups; thread t of 256 owns channels [4t, 4t+4) -> group t / (gsz/4)
+// ---------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+constexpr int kGnRowsPerBlock = 16;
+
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_stats_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt, int rows,
+                       int dim, double* __restrict__ stats) {
+    // dim == 1024: 32 channels per group == 8 consecutive threads
+    const int r0 = blockIdx.x * kGnRowsPerBlock;
+    const int r1 = min(r0 + kGnRowsPerBlock, rows);
+    const int group = threadIdx.x >> 3;
+    float s = 0.f, ss = 0.f;
+    int cur = -1;
+    auto flush = [&]() {
+        float a = s, c = ss;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if ((threadIdx.x & 7) == 0 && cur >= 0) {
+            atomicAdd(stats + (static_cast<size_t>(cur) * 32 + group) * 2 + 0,
+                      static_cast<double>(a));
+            atomicAdd(stats + (static_cast<size_t>(cur) * 32 + group) * 2 + 1,
+                      static_cast<double>(c));
+        }
+        s = 0.f;
+        ss = 0.f;
+    };
+    for (int r = r0; r < r1; ++r) {
+        const int u = row_utt[r];  // uniform across the block
+        if (u != cur) {
+            flush();
+            cur = u;
+        }
+        if (u < 0) continue;
+        const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * dim +
+                                                          threadIdx.x * 4);
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, ss);
+        ss = fmaf(v.y, v.y, ss);
+        ss = fmaf(v.z, v.z, ss);
+        ss = fmaf(v.w, v.w, ss);
+    }
+    flush();
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
+                             const int32_t* __restrict__ utt_len, int rows, int dim,
+                             const double* __restrict__ stats, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, OutT* __restrict__ out) {
+    const int group = threadIdx.x >> 3;
+    const int c0 = threadIdx.x * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    int cur = -1;
+    float mean = 0.f, rstd = 0.f;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int u = row_utt[r];
+        uint2 packed = make_uint2(0u, 0u);  // halo rows: zeros (conv padding)
+        if (u >= 0) {
+            if (u != cur) {
+                cur = u;
+                const double cnt = static_cast<double>(utt_len[u]) * (dim / 32);
+                const double m = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 0] / cnt;
+                double var = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 1] / cnt - m * m;
+                var = var < 0.0 ? 0.0 : var;
+                mean = static_cast<float>(m);
+                rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            }
+            const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * dim + c0);
+            float y[4] = {(v.x - mean) * rstd * g.x + bt.x, (v.y - mean) * rstd * g.y + bt.y,
+                          (v.z - mean) * rstd * g.z + bt.z, (v.w - mean) * rstd * g.w + bt.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = y[j] / (1.f + expf(-y[j]));  // x * sigmoid(x)
+            packed.x = Half16<OutT>::pack(y[0], y[1]);
+            packed.y = Half16<OutT>::pack(y[2], y[3]);
+        }
+        *reinterpret_cast<uint2*>(out + static_cast<size_t>(r) * dim + c0) = packed;
+    }
+}
+
+}  // namespace
+
+int launch_rmsnorm(int prec, const float* x, const float* w, int rows, int dim, float eps,
+                   void* out, cudaStream_t stream) {
+    return launch_rownorm<false>(prec, x, w, nullptr, rows, dim, eps, out, stream);
+}
+
+int launch_layernorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
+                     float eps, void* out, cudaStream_t stream) {
+    return launch_rownorm<true>(prec, x, w, b, rows, dim, eps, out, stream);
+}
+
+int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
+                           cudaStream_t stream) {
+    B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
+    if (rs.rows <= 0) return 0;
+    const int grid = (rs.rows + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
+    groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, rs.row_utt, rs.rows, dim, stats);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, int dim,
+                                 const double* stats, const float* gamma, const float* beta,
+                                 float eps, void* out, cudaStream_t stream) {
+    B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
+    if (rs.rows <= 0) return 0;
+    int grid = rs.rows < kNumSMs * 8 ? rs.rows : kNumSMs * 8;
+    if (prec == kPrecBf16)
+        groupnorm_apply_swish_kernel<__nv_bfloat16><<<grid, kGnThreads, 0, stream>>>(
+            x, rs.row_utt, rs.utt_len, rs.rows, dim, stats, gamma, beta, eps,
+            static_cast<__nv_bfloat16*>(out));
+    else if (prec == kPrecFp16)
+        groupnorm_apply_swish_kernel<__half><<<grid, kGnThreads, 0, stream>>>(
+            x, rs.row_utt, rs.utt_len, rs.rows, dim, stats, gamma, beta, eps,
+            static_cast<__half*>(out));
+    else {
+        set_error("groupnorm: unsupported precision %d", prec);
+        return 1;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200
