@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native codec decode path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+One "step" = one decode pass over one synthetic batch (BASELINE config 2 by default:
+16 utterances x 500 tokens = 160 audio-seconds, bf16 tensor-core operands), per GPU
+(weak scaling: every rank decodes its own batch; there is no data-path collective).
+Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "codec decode audio-sec/sec (device-timed)"
+UNIT = "audio-s/s"
+TOKEN_RATE = 50
+HOP = 320
+
+WORKLOADS = {
+    # name: (description, utterances, tokens per utterance)
+    "c1": ("4 clips x 5 s (BASELINE config 1, the reference's CPU case)", 4, 250),
+    "c2": ("16 clips x 10 s (BASELINE config 2)", 16, 500),
+    "c4": ("4 clips x 60 s long-form (BASELINE config 4)", 4, 3000),
+    "c5": ("64 windows x (100 context + 50 new) tokens (BASELINE config 5)", 64, 150),
+}
+
+LINEAR_FLOPS_PER_TOKEN = 373_854_208  # SURVEY.md 8a / BASELINE.md 4
+GEMM_FLOPS_PER_TOKEN = 4_194_304 + 14_680_064 + 50_331_648 + 301_989_888 + 2_625_536  # tcgen05 GEMM/conv kernel
+ATTN_FLOPS_PER_TOKEN_PER_T = 49_152
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"],
+                "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_ids(n_utts: int, tokens: int, seed: int):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 65536, (n_utts * tokens,), generator=g, dtype=torch.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle (CPU restatement of the reference algorithm)
+# ------------------------------------------------------------------------------------------------
+def cpu_decode_rate(tokens: int, clips: int, steps: int, warmup: int, seed: int = 1234):
+    """audio-s/s of the reference algorithm (oracle port, fp32, all host threads) on `clips` x `tokens`."""
+    import torch
+
+    from oracle import codec_oracle as O
+    from oracle import weights
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = weights.make_state_dict(seed=0, perturb=False)
+    ids = synthetic_ids(clips, tokens, seed).view(clips, tokens)
+    for _ in range(warmup):
+        O.decoder_forward(sd, ids)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.decoder_forward(sd, ids)
+        times.append(time.perf_counter() - t0)
+    audio_s = clips * tokens / TOKEN_RATE
+    mean = sum(times) / len(times)
+    return audio_s / mean, mean * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    desc, n_utts, tokens = WORKLOADS[args.workload]
+    clips = min(2, n_utts)  # bounded sample of the workload: `clips` of its utterances per step
+    value, ms, cores = cpu_decode_rate(tokens, clips, args.steps, max(args.warmup, 1))
+    sample = f"{clips} of the {n_utts} x {tokens}-token utterances per step (same ids seed), oracle port of the reference algorithm, fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "sample": sample, "weights": "random-init (oracle.weights seed 0)"},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from tts_max_b200.codec import decoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tts_max_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    desc, n_utts, tokens = WORKLOADS[args.workload]
+    seqlens = [tokens] * n_utts
+    total_tokens = n_utts * tokens
+    audio_s = total_tokens / TOKEN_RATE
+
+    dec = decoder.Decoder(16000, HOP, None, None, precision=args.precision, init_seed=0)
+    dec.to(dev).eval()
+    ids_host = synthetic_ids(n_utts, tokens, 1234 + rank).pin_memory()
+    ids_dev = ids_host.to(dev)
+    wav_host = torch.empty(total_tokens * HOP, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(max(args.warmup, 3)):
+        dec.decode_packed_device(ids_dev, seqlens)
+    barrier()
+    launches0 = dec.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush between timed steps (outside the per-step event bracket)
+            starts[i].record()
+            wav = dec.decode_packed_device(ids_dev, seqlens)
+            ends[i].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = dec.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    dev_ms_total = sum(step_ms)
+    assert torch.isfinite(wav[:4096]).all()
+
+    # ---- end to end through the public host-buffer API ("e2e") ----
+    for _ in range(2):
+        dec.decode_packed_host(ids_host, seqlens, out=wav_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode_packed_host(ids_host, seqlens, out=wav_host)  # H2D ids, decode, D2H PCM, sync
+    barrier()
+    e2e_s_total = time.perf_counter() - t0
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms_total, e2e_s_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_total, e2e_s_total = t.tolist()
+
+    ms_per_step = dev_ms_total / args.steps
+    value = world * audio_s / (ms_per_step / 1e3)
+    e2e_value = world * audio_s * args.steps / e2e_s_total
+
+    # ---- per-stage device times (separate profiling pass, never inside the timed region) ----
+    roofline = None
+    stage_ms = {}
+    cpu_baseline = None
+    if rank == 0:
+        dec.profile(True)
+        prof_steps = 3
+        for _ in range(prof_steps):
+            dec.decode_packed_device(ids_dev, seqlens)
+        torch.cuda.synchronize(dev)
+        stage_ms = {k: v / prof_steps for k, v in dec.stage_times().items()}
+        dec.profile(False)
+        peaks = read_peaks()
+        gemm_ms = sum(v for k, v in stage_ms.items() if k.endswith("_gemm"))
+        n_gemm = 1 + 1 + 8 + 12 * 4 + 1  # fc_post_a, embed, 8 conv3, 48 transformer linears, head
+        gemm_flops = GEMM_FLOPS_PER_TOKEN * total_tokens
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["tflops_sustained"]
+        step_flops = (LINEAR_FLOPS_PER_TOKEN + ATTN_FLOPS_PER_TOKEN_PER_T * tokens) * total_tokens
+        roofline = {
+            "kernel": "gemm_tc05_kernel (tcgen05 GEMM / implicit conv1d; all dense layers)",
+            "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+            "frac": round(achieved / peak, 4), "traffic": None,
+            "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+            "launches_per_step": n_gemm, "avg_launch_ms": round(gemm_ms / n_gemm, 4),
+            "flops_per_step": gemm_flops,
+            "share_of_step": round(gemm_ms / max(sum(stage_ms.values()), 1e-9), 4),
+            "whole_step": {"flops": step_flops, "achieved": round(step_flops / (ms_per_step / 1e3) / 1e12, 1),
+                           "frac": round(step_flops / (ms_per_step / 1e3) / 1e12 / peak, 4)},
+        }
+        if not args.no_cpu_baseline:
+            clips = min(2, n_utts)
+            v, ms, cores = cpu_decode_rate(tokens, clips, steps=3, warmup=1)
+            cpu_baseline = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{clips} of the {n_utts} x {tokens}-token utterances, 3 timed passes after 1 warm-up "
+                                      f"({ms:.0f} ms each), oracle port of the reference algorithm, fp32, torch CPU"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "utterances_per_gpu": n_utts, "tokens_per_utterance": tokens,
+                       "audio_seconds_per_step_per_gpu": audio_s, "weights": "random-init, reference distributions (seed 0)",
+                       "parallelism": f"dp{world} (independent utterances, no data-path collective)",
+                       "l2": "256 MiB device buffer written between timed steps (outside the per-step event bracket)",
+                       "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8 * world,
+                    "d2h_bytes_per_step": wav_host.numel() * 4 * world,
+                    "api": "Decoder.decode_packed_host -> b200codec_decode_host (pinned host ids in, pinned host PCM out, sync inside)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
+            "wall_s_timed_region": round(t_wall, 4),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+"""GPU: the whole decode path through the reference-facing API against the reference's golden
+vectors and the oracle, plus the size-independent properties at BASELINE config sizes.
+
+Stated tolerances (vs the fp32 reference, weights = oracle.weights seed 0):
+  bf16 operands: SNR >= 30 dB and max-abs <= 5e-2 * peak   (BASELINE "bf16 decode" tolerance)
+  fp16 operands: SNR >= 45 dB and max-abs <= 1e-2 * peak
+The FSQ lookup inside is bit-exact (tests/test_gpu_kernels.py).
+"""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import codec_oracle as O
+from oracle import weights
+from tts_max_b200.codec import decoder, decoding
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16": (30.0, 5e-2), "fp16": (45.0, 1e-2)}
+
+
+def check_wave(ref, got, prec, what=""):
+    snr_min, rel = TOL[prec]
+    snr = O.snr_db(ref, got)
+    peak = ref.abs().max().item()
+    maxabs = (ref.double() - got.double()).abs().max().item()
+    print(f"[parity] {what} {prec}: SNR {snr:.1f} dB, max-abs {maxabs:.3e}, peak {peak:.3e}")
+    assert torch.isfinite(got).all()
+    assert snr >= snr_min, f"{what}: SNR {snr:.1f} dB < {snr_min}"
+    assert maxabs <= rel * peak, f"{what}: max-abs {maxabs:.3e} > {rel} * peak {peak:.3e}"
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["u37", "u5", "u1"])
+def test_forward_vs_reference_golden(gpu_decoders, golden, prec, name):
+    d = gpu_decoders[prec]
+    ids = torch.from_numpy(golden[f"{name}_ids"])
+    wav = d(ids.view(1, -1).cuda())
+    assert wav.shape == (1, 1, 320 * ids.numel()) and wav.dtype == torch.float32 and wav.is_cuda
+    check_wave(torch.from_numpy(golden[f"{name}_wav"])[0], wav[0, 0].cpu(), prec, name)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_batched_forward_vs_reference_golden(gpu_decoders, golden, prec):
+    d = gpu_decoders[prec]
+    ids = torch.from_numpy(golden["b2x24_ids"]).cuda()
+    wav = d(ids)                       # (B, T)
+    wav3 = d(ids.unsqueeze(1))         # (B, 1, T)
+    assert wav.shape == (2, 1, 320 * 24)
+    assert torch.equal(wav, wav3)
+    check_wave(torch.from_numpy(golden["b2x24_wav"]), wav.cpu(), prec, "b2x24")
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_config1_vs_oracle(gpu_decoders, state_dict, prec):
+    """BASELINE config 1: 4 clips x 5 s against the fp32 CPU oracle."""
+    d = gpu_decoders[prec]
+    ids = torch.randint(0, 65536, (4, 250), generator=torch.Generator().manual_seed(1234))
+    ref = O.decoder_forward(state_dict, ids)
+    wav = d(ids.cuda()).cpu()
+    check_wave(ref, wav, prec, "config1 4x250")
+
+
+def test_audio_decoder_decode_contract(tmp_path, state_dict, golden):
+    """decoding.create(...).decode(ids) -> (1, 320 T) float32 CPU, both checkpoint layouts."""
+    outs = []
+    for layout in ("xcodec2", "ttsmax"):
+        dirp = tmp_path / layout
+        dirp.mkdir()
+        ckpt = weights.to_xcodec2_checkpoint(state_dict) if layout == "xcodec2" else weights.to_ttsmax_checkpoint(state_dict)
+        torch.save(ckpt, dirp / "ckpt.pt")
+        (dirp / "model_config.json").write_text(json.dumps(
+            {"sample_rate": 16000, "token_rate": 50, "hop_length": 320, "upsample_factors": None, "kernel_sizes": None}))
+        dec = decoding.create(str(dirp / "ckpt.pt"), device="cuda")
+        assert dec.sample_rate == 16000 and dec.token_rate == 50
+        ids = torch.from_numpy(golden["u37_ids"])
+        wav = dec.decode(ids)
+        assert wav.shape == (1, 320 * 37) and wav.dtype == torch.float32 and wav.device.type == "cpu"
+        check_wave(torch.from_numpy(golden["u37_wav"]), wav, "bf16", f"decode {layout}")
+        wav_dev_ids = dec.decode(ids.cuda())            # rewards.py passes device ids
+        assert torch.equal(wav, wav_dev_ids)
+        wav_i32 = dec.decode(ids.to(torch.int32))
+        assert torch.equal(wav, wav_i32)
+        outs.append(wav)
+        sd = dec._decoder.state_dict()
+        assert all(torch.equal(sd[k], state_dict[k]) for k in state_dict)
+        del dec
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_varlen_batch_equals_single_decodes(gpu_decoders):
+    """Packed varlen decode reproduces each utterance's single decode (no padding semantics)."""
+    d = gpu_decoders["bf16"]
+    g = torch.Generator().manual_seed(77)
+    lens = [1, 2, 3, 17, 64, 65, 129, 250]
+    utts = [torch.randint(0, 65536, (n,), generator=g) for n in lens]
+    packed = d.decode_packed_host(torch.cat(utts), lens)
+    off = 0
+    for ids in utts:
+        single = d.decode_packed_host(ids, [ids.numel()])
+        got = packed[off * 320:(off + ids.numel()) * 320]
+        assert got.shape == single.shape
+        # identical kernels and K order per row; only fp64 GroupNorm atomics may reorder
+        assert (got - single).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item()), ids.numel()
+        off += ids.numel()
+
+
+def test_row_of_batch_equals_single(gpu_decoders):
+    d = gpu_decoders["bf16"]
+    ids = torch.randint(0, 65536, (3, 100), generator=torch.Generator().manual_seed(8)).cuda()
+    batch = d(ids)
+    for b in range(3):
+        single = d(ids[b:b + 1])
+        assert (batch[b] - single[0]).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item())
+
+
+def test_determinism(gpu_decoders):
+    d = gpu_decoders["bf16"]
+    ids = torch.randint(0, 65536, (2, 300), generator=torch.Generator().manual_seed(9)).cuda()
+    a = d(ids).clone()
+    b = d(ids)
+    assert (a - b).abs().max().item() <= 1e-6 * max(1e-3, a.abs().max().item())
+
+
+def test_errors_are_python_exceptions(gpu_decoders, tmp_path):
+    d = gpu_decoders["bf16"]
+    with pytest.raises(ValueError):
+        d.decode_packed_host(torch.tensor([5, 70000, 3]), [3])          # out of range, host path
+    with pytest.raises(ValueError):
+        d.decode_packed_host(torch.tensor([5, -1, 3]), [3])
+    with pytest.raises(ValueError):
+        d.decode_packed_host(torch.tensor([5, 1, 3]), [3, 0])           # empty utterance
+    cfg = decoding.DecoderConfig("", 16000, 50, 320, None, None)
+    dec = decoding.AudioDecoder(None, cfg, device="cuda")
+    with pytest.raises(ValueError):
+        dec.decode(torch.tensor([], dtype=torch.int64))
+    with pytest.raises(ValueError):
+        dec.decode(torch.tensor([1, 2, 65536]).cuda())                  # device path: flagged by the kernel
+    assert dec.decode(torch.tensor([1, 2, 3])).shape == (1, 960)         # still usable afterwards
+
+
+@pytest.mark.parametrize("shape", [(16, 500), (4, 3000)])
+def test_full_size_properties(gpu_decoders, shape):
+    """BASELINE configs 2 and 4 at full size: shape/finite, row-of-batch == single decode
+    (a size-independent property; the oracle takes tens of seconds to minutes at these sizes)."""
+    d = gpu_decoders["bf16"]
+    B, T = shape
+    ids = torch.randint(0, 65536, (B, T), generator=torch.Generator().manual_seed(B * T)).cuda()
+    wav = d(ids)
+    assert wav.shape == (B, 1, 320 * T) and torch.isfinite(wav).all()
+    single = d(ids[B - 1:B])
+    assert (wav[B - 1] - single[0]).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item())
+    assert wav.abs().max().item() < 1e3
+
+
+def test_config2_vs_oracle_subsample(gpu_decoders, state_dict):
+    """BASELINE config 2 (16 x 10 s, bf16): two of the sixteen clips checked against the oracle."""
+    ids = torch.randint(0, 65536, (16, 500), generator=torch.Generator().manual_seed(1234))
+    for prec in ("bf16", "fp16"):
+        wav = gpu_decoders[prec](ids.cuda()).cpu()
+        ref = O.decoder_forward(state_dict, ids[[0, 15]])
+        check_wave(ref, wav[[0, 15]], prec, "config2 rows 0,15")
+
+
+def test_streaming_windows_config5(gpu_decoders, state_dict):
+    """BASELINE config 5: 64 windows of (100 context + 50 new) tokens; the oracle is the reference
+    forward on the same window, trimmed to the last 16000 samples."""
+    d = gpu_decoders["bf16"]
+    ids = torch.randint(0, 65536, (64, 150), generator=torch.Generator().manual_seed(5))
+    wav = d(ids.cuda()).cpu()[:, 0, -16000:]
+    ref = O.decoder_forward(state_dict, ids[:2])[:, 0, -16000:]
+    check_wave(ref, wav[:2], "bf16", "config5 windows 0,1")

@@ -216,7 +216,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 if (p.act == kActSilu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));  // MUFU.EX2 + MUFU.RCP
                 }
                 if (row_ok) {
                     if (p.residual != nullptr) {

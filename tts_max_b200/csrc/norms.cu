@@ -116,47 +116,39 @@ int launch_rownorm(int prec, const float* x, const float* w, const float* b, int
 constexpr int kGnThreads = 256;
 constexpr int kGnRowsPerBlock = 16;
 
+// One CTA reduces rows [q0 + 16*y, +16) of one utterance (work item {row0, T, q0} shared with
+// the attention tile list). The chunking is relative to the utterance start, so the fp32
+// partial sums -- and with them the whole decode -- do not depend on where in a batch the
+// utterance sits (row-of-batch == single decode).
 __global__ void __launch_bounds__(kGnThreads)
-groupnorm_stats_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt, int rows,
-                       int dim, double* __restrict__ stats) {
+groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ work, int dim,
+                       double* __restrict__ stats, const int32_t* __restrict__ row_utt) {
     // dim == 1024: 32 channels per group == 8 consecutive threads
-    const int r0 = blockIdx.x * kGnRowsPerBlock;
-    const int r1 = min(r0 + kGnRowsPerBlock, rows);
+    const int4 wk = work[blockIdx.x];
+    const int t0 = wk.z + blockIdx.y * kGnRowsPerBlock;
+    const int t1 = min(t0 + kGnRowsPerBlock, min(wk.z + kAttnBlockQ, wk.y));
+    if (t0 >= t1) return;
+    const int utt = row_utt[wk.x];
     const int group = threadIdx.x >> 3;
     float s = 0.f, ss = 0.f;
-    int cur = -1;
-    auto flush = [&]() {
-        float a = s, c = ss;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
-        if ((threadIdx.x & 7) == 0 && cur >= 0) {
-            atomicAdd(stats + (static_cast<size_t>(cur) * 32 + group) * 2 + 0,
-                      static_cast<double>(a));
-            atomicAdd(stats + (static_cast<size_t>(cur) * 32 + group) * 2 + 1,
-                      static_cast<double>(c));
-        }
-        s = 0.f;
-        ss = 0.f;
-    };
-    for (int r = r0; r < r1; ++r) {
-        const int u = row_utt[r];  // uniform across the block
-        if (u != cur) {
-            flush();
-            cur = u;
-        }
-        if (u < 0) continue;
-        const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * dim +
-                                                          threadIdx.x * 4);
+    for (int t = t0; t < t1; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(
+            x + static_cast<size_t>(wk.x + t) * dim + threadIdx.x * 4);
         s += (v.x + v.y) + (v.z + v.w);
         ss = fmaf(v.x, v.x, ss);
         ss = fmaf(v.y, v.y, ss);
         ss = fmaf(v.z, v.z, ss);
         ss = fmaf(v.w, v.w, ss);
     }
-    flush();
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 7) == 0) {
+        atomicAdd(stats + (static_cast<size_t>(utt) * 32 + group) * 2 + 0, static_cast<double>(s));
+        atomicAdd(stats + (static_cast<size_t>(utt) * 32 + group) * 2 + 1, static_cast<double>(ss));
+    }
 }
 
 template <typename OutT>
@@ -211,9 +203,10 @@ int launch_layernorm(int prec, const float* x, const float* w, const float* b, i
 int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
                            cudaStream_t stream) {
     B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
-    if (rs.rows <= 0) return 0;
-    const int grid = (rs.rows + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
-    groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, rs.row_utt, rs.rows, dim, stats);
+    if (rs.n_attn_work <= 0) return 0;
+    static_assert(kAttnBlockQ % kGnRowsPerBlock == 0, "GroupNorm chunks must tile the work item");
+    dim3 grid(rs.n_attn_work, kAttnBlockQ / kGnRowsPerBlock);
+    groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, rs.attn_work, dim, stats, rs.row_utt);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
