@@ -68,15 +68,16 @@ class ClockSampler:
         self._thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                     "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            return
+        self._proc = proc
+        for line in proc.stdout:
+            if self._stop.is_set():
+                break
+            self.rows.append([c.strip() for c in line.split(",")])
 
     def __enter__(self):
         self._thread.start()
@@ -84,6 +85,9 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self._stop.set()
+        proc = getattr(self, "_proc", None)
+        if proc is not None:
+            proc.kill()
         self._thread.join(timeout=10)
 
     def summary(self):
@@ -202,6 +206,7 @@ def run_ours(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
+        time.sleep(0.15)  # let the sampler start
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()  # L2 flush between timed steps (outside the per-step event bracket)
@@ -301,7 +306,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

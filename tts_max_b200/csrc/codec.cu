@@ -424,7 +424,6 @@ int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, v
     c.ld_res = ldc;
     c.row_valid = mask_rows ? h->rs.row_valid : nullptr;
     c.act = act;
-    c.row_sumsq = nullptr;
     return launch_gemm(c, s);
 }
 
@@ -944,7 +943,6 @@ int b200codec_gemm(int precision, const void* a_dev, const void* w_dev, int M, i
     c.ld_res = ld_res;
     c.row_valid = nullptr;
     c.act = act;
-    c.row_sumsq = nullptr;
     B200_CHECK(c.n_store <= ldc, "gemm: ldc (%d) must cover N rounded up to 32 (%d)", ldc, c.n_store);
     return launch_gemm(c, static_cast<cudaStream_t>(stream));
 }

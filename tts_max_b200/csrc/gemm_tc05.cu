@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptor encoding, dispatch, weight repacking.
 #include "gemm_tc05.cuh"
+#include "gemm_tc05_2cta.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -100,9 +101,16 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
     return 0;
 }
 
-static bool gemm_is_wide(const GemmCall& c) {
-    return c.n_store >= 1024 && (c.n_store % 256 == 0);
+// kernel selection: CTA pairs (256x256 per cluster) whenever N tiles evenly and there is more
+// than one 128-row tile of work; the 1-CTA kernel covers small M and the ragged head GEMM.
+enum GemmKind { kGemm1CtaN128 = 0, kGemm1CtaN256 = 1, kGemm2Cta = 2 };
+static GemmKind gemm_kind(const GemmCall& c) {
+    const bool n256 = c.n_store >= 256 && (c.n_store % 256 == 0);
+    if (n256 && c.a_rows > 128) return kGemm2Cta;
+    if (n256 && c.n_store >= 1024) return kGemm1CtaN256;
+    return kGemm1CtaN128;
 }
+static bool gemm_is_wide(const GemmCall& c) { return gemm_kind(c) == kGemm1CtaN256; }
 
 int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out) {
     const int dt = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
@@ -126,6 +134,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     B200_CHECK(c.n_store % 32 == 0 && c.n_store <= c.ldc, "gemm: bad n_store %d (ldc %d)",
                c.n_store, c.ldc);
     B200_CHECK(c.taps >= 1 && c.taps % 2 == 1, "gemm: taps must be odd");
+    B200_CHECK(c.residual == nullptr || c.out_fp32, "gemm: a residual requires fp32 output");
     if (c.a_rows <= 0) return 0;
     const bool wide = gemm_is_wide(c);
     alignas(64) CUtensorMap ta, tb;
@@ -145,7 +154,13 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     p.ld_res = c.ld_res;
     p.row_valid = c.row_valid;
     p.act = c.act;
-    p.row_sumsq = c.row_sumsq;
+    if (gemm_kind(c) == kGemm2Cta) {
+        if (c.precision == kPrecBf16)
+            return c.out_fp32 ? launch_gemm_tc05_2cta<__nv_bfloat16, float>(ta, tb, p, stream)
+                              : launch_gemm_tc05_2cta<__nv_bfloat16, __nv_bfloat16>(ta, tb, p, stream);
+        return c.out_fp32 ? launch_gemm_tc05_2cta<__half, float>(ta, tb, p, stream)
+                          : launch_gemm_tc05_2cta<__half, __half>(ta, tb, p, stream);
+    }
     if (c.precision == kPrecBf16) return dispatch<__nv_bfloat16>(c, ta, tb, p, wide, stream);
     return dispatch<__half>(c, ta, tb, p, wide, stream);
 }

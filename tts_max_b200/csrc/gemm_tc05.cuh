@@ -44,7 +44,6 @@ struct GemmParams {
     int ld_res;
     const uint8_t* row_valid;  // [M] or nullptr; rows flagged 0 are written as zeros
     int act;
-    float* row_sumsq;      // optional [M]: atomically accumulates sum_n out[m,n]^2 (RMSNorm fusion)
 };
 
 constexpr int kGemmBlockM = 128;
@@ -190,7 +189,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const bool row_zero = row_ok && p.row_valid != nullptr && p.row_valid[row] == 0;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc05_fence_after();
-            float sumsq = 0.f;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 const int n0 = n_blk * BLOCK_N + c * 32;
@@ -235,10 +233,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 0.f;
                     }
-                    if (p.row_sumsq != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sumsq = fmaf(v[j], v[j], sumsq);
-                    }
                     OutT* dst = out + static_cast<size_t>(row) * p.ldc + n0;
                     if constexpr (sizeof(OutT) == 4) {
                         float4* d4 = reinterpret_cast<float4*>(dst);
@@ -259,7 +253,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
             }
-            if (p.row_sumsq != nullptr && row_ok) atomicAdd(p.row_sumsq + row, sumsq);
             tc05_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) {

@@ -86,7 +86,6 @@ struct GemmCall {
     int ld_res;
     const uint8_t* row_valid;
     int act;
-    float* row_sumsq;
     // optional pre-encoded TMA descriptors (CUtensorMap, 128 B each, 64-byte aligned);
     // when null they are encoded on the fly.
     const void* tmap_a = nullptr;
