@@ -114,8 +114,8 @@ struct B200Codec {
     // workspace (grow-only)
     DevBuf ws;
     int ws_rows = 0;
-    void *a0, *xc, *an, *qkv, *y, *f;  // operand dtype
-    float *x, *hbuf, *ho;
+    void *a0, *xc, *an, *qkv, *y, *f, *xb;  // operand dtype
+    float *x, *hbuf, *ho, *ss;
     double* gn_stats = nullptr;
     size_t gn_stats_bytes = 0;
     // plan (row space) cache
@@ -342,7 +342,8 @@ int ensure_workspace(B200Codec* h, int rows) {
     auto al = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
     size_t sz_a0 = al(R * h->V * es), sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
            sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(R * kHeadLd * 4);
-    size_t total = sz_a0 + 3 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho;
+    size_t sz_ss = al(R * 8 * 4);
+    size_t total = sz_a0 + 4 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho + sz_ss;
     h->ws.release();
     h->ws_rows = 0;
     if (h->ws.ensure(total)) return 1;
@@ -352,11 +353,13 @@ int ensure_workspace(B200Codec* h, int rows) {
     h->xc = p; p += sz_c;
     h->an = p; p += sz_c;
     h->y = p; p += sz_c;
+    h->xb = p; p += sz_c;
     h->qkv = p; p += sz_qkv;
     h->f = p; p += sz_f;
     h->x = reinterpret_cast<float*>(p); p += sz_x;
     h->hbuf = reinterpret_cast<float*>(p); p += sz_x;
     h->ho = reinterpret_cast<float*>(p); p += sz_ho;
+    h->ss = reinterpret_cast<float*>(p); p += sz_ss;
     h->ws_rows = static_cast<int>(R);
     return 0;
 }
@@ -404,9 +407,16 @@ void collect_timers(B200Codec* h) {
         h->launches++;           \
     } while (0)
 
+// RMSNorm fusion hooks of one GEMM call (all optional)
+struct NormFuse {
+    const float* ss_in = nullptr;  // consume: scale rows by rsqrt(mean(x^2) + eps)
+    void* out16 = nullptr;         // produce: 16-bit copy of the fp32 result ...
+    float* ss_out = nullptr;       // ... and its per-row sum-of-squares partials
+};
+
 int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
          bool out_fp32, int ldc, int n_store, const float* bias, const float* residual, int act,
-         bool mask_rows, cudaStream_t s) {
+         bool mask_rows, cudaStream_t s, const NormFuse& nf = NormFuse()) {
     GemmCall c;
     c.precision = h->cfg.precision;
     c.a = a;
@@ -424,10 +434,17 @@ int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, v
     c.ld_res = ldc;
     c.row_valid = mask_rows ? h->rs.row_valid : nullptr;
     c.act = act;
+    c.ss_in = nf.ss_in;
+    c.ss_inv_dim = 1.f / static_cast<float>(h->C);
+    c.ss_eps = 1e-6f;
+    c.out16 = nf.out16;
+    c.ld16 = h->C;
+    c.ss_out = nf.ss_out;
     return launch_gemm(c, s);
 }
 
-int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t s) {
+int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t s,
+                 const NormFuse& nf = NormFuse()) {
     const int C = h->C, prec = h->cfg.precision;
     const RowSpace& rs = h->rs;
     double* st1 = h->gn_stats + static_cast<size_t>(stats_slot) * rs.n_utts * 64;
@@ -448,7 +465,7 @@ int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t 
     }
     {
         Stage t(h, "conv3_gemm", s);
-        RUN(gemm(h, h->an, C, w.w2, C, 3, h->x, true, C, C, w.b2, h->x, kActNone, false, s));
+        RUN(gemm(h, h->an, C, w.w2, C, 3, h->x, true, C, C, w.b2, h->x, kActNone, false, s, nf));
     }
     return 0;
 }
@@ -475,18 +492,30 @@ int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cuda
         RUN(gemm(h, h->xc, C, h->w_embed, C, 7, h->x, true, C, C,
                  h->m("decoder.backbone.embed.bias"), nullptr, kActNone, false, s));
     }
+    // RMSNorm fusion (bf16 operands, CTA-pair GEMM): the GEMM that produces the residual stream x
+    // also emits bf16(x) and per-row sum-of-squares partials; the norm weight lives in the columns
+    // of c_attn / fc1 and rstd[row] is applied in their epilogues. fp16 operands keep a standalone
+    // normalisation (un-normalised activations could leave fp16's range).
+    const bool fuse_rms = prec == kPrecBf16 && gemm_uses_cta_pairs(rs.rows, C);
+    NormFuse produce, consume;
+    if (fuse_rms) {
+        produce.out16 = h->xb;
+        produce.ss_out = h->ss;
+        consume.ss_in = h->ss;
+    }
     if (resnet_block(h, h->res[0], 0, s)) return 1;
-    if (resnet_block(h, h->res[1], 2, s)) return 1;
+    if (resnet_block(h, h->res[1], 2, s, produce)) return 1;
     for (int l = 0; l < h->L; ++l) {
         const LayerW& w = h->layers[l];
-        {
+        const bool last = l + 1 == h->L;
+        if (!fuse_rms) {
             Stage t(h, "rmsnorm", s);
-            RUN(launch_rmsnorm(prec, h->x, w.att_norm, rs.rows, C, 1e-6f, h->an, s));
+            RUN(launch_rmsnorm(prec, h->x, nullptr, rs.rows, C, 1e-6f, h->an, s));
         }
         {
             Stage t(h, "qkv_gemm", s);
-            RUN(gemm(h, h->an, C, w.qkv, 3 * C, 1, h->qkv, false, 3 * C, 3 * C, nullptr, nullptr,
-                     kActNone, false, s));
+            RUN(gemm(h, fuse_rms ? h->xb : h->an, C, w.qkv, 3 * C, 1, h->qkv, false, 3 * C, 3 * C,
+                     nullptr, nullptr, kActNone, false, s, consume));
         }
         {
             Stage t(h, "attention", s);
@@ -494,20 +523,22 @@ int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cuda
         }
         {
             Stage t(h, "proj_gemm", s);
-            RUN(gemm(h, h->y, C, w.proj, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s));
+            RUN(gemm(h, h->y, C, w.proj, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s,
+                     produce));
         }
-        {
+        if (!fuse_rms) {
             Stage t(h, "rmsnorm", s);
-            RUN(launch_rmsnorm(prec, h->x, w.ffn_norm, rs.rows, C, 1e-6f, h->an, s));
+            RUN(launch_rmsnorm(prec, h->x, nullptr, rs.rows, C, 1e-6f, h->an, s));
         }
         {
             Stage t(h, "fc1_gemm", s);
-            RUN(gemm(h, h->an, C, w.fc1, 4 * C, 1, h->f, false, 4 * C, 4 * C, nullptr, nullptr,
-                     kActSilu, false, s));
+            RUN(gemm(h, fuse_rms ? h->xb : h->an, C, w.fc1, 4 * C, 1, h->f, false, 4 * C, 4 * C,
+                     nullptr, nullptr, kActSilu, false, s, consume));
         }
         {
             Stage t(h, "fc2_gemm", s);
-            RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s));
+            RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s,
+                     last ? NormFuse() : produce));
         }
     }
     if (resnet_block(h, h->res[2], 4, s)) return 1;
@@ -785,9 +816,11 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
         B200_CUDA_OK(cudaMemcpyAsync(scratch, h->m(p + "att.c_attn.weight"), 3ull * C * C * 4,
                                      cudaMemcpyDeviceToDevice, s));
         if (launch_fold_rope(scratch, h->H, C / h->H, C, h->rope_cos, h->rope_sin, s)) return 1;
-        if (launch_repack_weight(prec, scratch, w.qkv, 3 * C, C, 1, s)) return 1;
+        // RMSNorm weights are folded into the columns of the consuming Linear:
+        // (x * rstd * g) W^T == rstd * (x (W diag(g))^T)   (decoder_modules.py:233-236, 312-313)
+        if (launch_repack_weight(prec, scratch, w.qkv, 3 * C, C, 1, s, w.att_norm)) return 1;
         if (launch_repack_weight(prec, h->m(p + "att.c_proj.weight"), w.proj, C, C, 1, s)) return 1;
-        if (launch_repack_weight(prec, h->m(p + "mlp.fc1.weight"), w.fc1, 4 * C, C, 1, s)) return 1;
+        if (launch_repack_weight(prec, h->m(p + "mlp.fc1.weight"), w.fc1, 4 * C, C, 1, s, w.ffn_norm)) return 1;
         if (launch_repack_weight(prec, h->m(p + "mlp.fc2.weight"), w.fc2, C, 4 * C, 1, s)) return 1;
     }
     h->w_head = take(n_head);

@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kFsqThreads = 256;
 constexpr int kFsqChanPerThread = 8;
+constexpr int kFsqRowsPerBlock = 32;
 
 template <typename OutT>
 __device__ __forceinline__ void store8(OutT* dst, const float (&v)[8]);
@@ -71,7 +72,12 @@ fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_t
         b[i] = __ldg(b_out + c0 + i);
     }
 
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    // each CTA owns a contiguous slab of rows, so the 72 KB weight block it holds in registers is
+    // fetched once per kFsqRowsPerBlock rows instead of once per handful of rows
+    const int r_begin = blockIdx.x * kFsqRowsPerBlock;
+    const int r_end = min(r_begin + kFsqRowsPerBlock, rows);
+#pragma unroll 2
+    for (int r = r_begin; r < r_end; ++r) {
         const int tok = row_tok ? row_tok[r] : r;
         float v[kFsqChanPerThread];
         if (tok < 0) {
@@ -109,8 +115,7 @@ int launch_typed(const void* ids, int id_type, const int32_t* row_tok, int rows,
     if (rows <= 0) return 0;
     const int chan_blocks = (channels + kFsqThreads * kFsqChanPerThread - 1) /
                             (kFsqThreads * kFsqChanPerThread);
-    int gx = rows < kNumSMs * 8 ? rows : kNumSMs * 8;  // 8 resident CTAs per SM
-    dim3 grid(gx, chan_blocks);
+    dim3 grid((rows + kFsqRowsPerBlock - 1) / kFsqRowsPerBlock, chan_blocks);
     if (id_type == 1)
         fsq_lookup_kernel<OutT, long long><<<grid, kFsqThreads, 0, stream>>>(
             static_cast<const long long*>(ids), row_tok, rows, w_out, b_out, channels,

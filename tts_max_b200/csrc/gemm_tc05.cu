@@ -27,7 +27,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 template <typename T>
 __global__ void repack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int N,
-                                     int Cin, int taps) {
+                                     int Cin, int taps, const float* __restrict__ col_scale) {
     // dst[n, tap*Cin + c] = src[n, c, tap]
     const size_t total = static_cast<size_t>(N) * Cin * taps;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -36,7 +36,8 @@ __global__ void repack_weight_kernel(const float* __restrict__ src, T* __restric
         const size_t rest = i / Cin;
         const int tap = static_cast<int>(rest % taps);
         const size_t n = rest / taps;
-        const float v = src[(n * Cin + c) * taps + tap];
+        float v = src[(n * Cin + c) * taps + tap];
+        if (col_scale != nullptr) v *= col_scale[c];
         dst[i] = Half16<T>::from_float(v);
     }
 }
@@ -101,16 +102,23 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
     return 0;
 }
 
-// kernel selection: CTA pairs (256x256 per cluster) whenever N tiles evenly and there is more
-// than one 128-row tile of work; the 1-CTA kernel covers small M and the ragged head GEMM.
+// kernel selection: CTA pairs (256x256 per cluster) whenever N tiles evenly -- for every M, so
+// an utterance sees the same arithmetic alone or inside a batch; the 1-CTA kernel covers the
+// ragged head GEMM (N = 1282).
 enum GemmKind { kGemm1CtaN128 = 0, kGemm1CtaN256 = 1, kGemm2Cta = 2 };
 static GemmKind gemm_kind(const GemmCall& c) {
     const bool n256 = c.n_store >= 256 && (c.n_store % 256 == 0);
-    if (n256 && c.a_rows > 128) return kGemm2Cta;
+    if (n256) return kGemm2Cta;
     if (n256 && c.n_store >= 1024) return kGemm1CtaN256;
     return kGemm1CtaN128;
 }
 static bool gemm_is_wide(const GemmCall& c) { return gemm_kind(c) == kGemm1CtaN256; }
+bool gemm_uses_cta_pairs(int a_rows, int n_store) {
+    GemmCall c{};
+    c.a_rows = a_rows;
+    c.n_store = n_store;
+    return gemm_kind(c) == kGemm2Cta;
+}
 
 int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out) {
     const int dt = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
@@ -154,6 +162,17 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     p.ld_res = c.ld_res;
     p.row_valid = c.row_valid;
     p.act = c.act;
+    p.ss_in = c.ss_in;
+    p.ss_inv_dim = c.ss_inv_dim;
+    p.ss_eps = c.ss_eps;
+    p.out16 = c.out16;
+    p.ld16 = c.ld16;
+    p.ss_out = c.ss_out;
+    const bool fused = c.ss_in != nullptr || c.out16 != nullptr || c.ss_out != nullptr;
+    B200_CHECK(!fused || gemm_kind(c) == kGemm2Cta,
+               "gemm: the RMSNorm-fused epilogue needs the CTA-pair kernel (N % 256 == 0)");
+    B200_CHECK((c.out16 == nullptr && c.ss_out == nullptr) || (c.out_fp32 && c.n_store == 1024),
+               "gemm: out16 / ss_out require fp32 output with N == 1024");
     if (gemm_kind(c) == kGemm2Cta) {
         if (c.precision == kPrecBf16)
             return c.out_fp32 ? launch_gemm_tc05_2cta<__nv_bfloat16, float>(ta, tb, p, stream)
@@ -166,16 +185,16 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
 }
 
 int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const float* col_scale) {
     const size_t total = static_cast<size_t>(N) * Cin * taps;
     if (total == 0) return 0;
     const int grid = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     if (prec == kPrecBf16)
         repack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-            src, static_cast<__nv_bfloat16*>(dst), N, Cin, taps);
+            src, static_cast<__nv_bfloat16*>(dst), N, Cin, taps, col_scale);
     else if (prec == kPrecFp16)
         repack_weight_kernel<__half><<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), N,
-                                                               Cin, taps);
+                                                               Cin, taps, col_scale);
     else {
         set_error("repack: unsupported precision %d", prec);
         return 1;

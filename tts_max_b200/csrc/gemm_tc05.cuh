@@ -44,6 +44,15 @@ struct GemmParams {
     int ld_res;
     const uint8_t* row_valid;  // [M] or nullptr; rows flagged 0 are written as zeros
     int act;
+    // ---- RMSNorm fusion (CTA-pair kernel only) ----
+    // consumer: out = act(rstd[m] * acc + bias), rstd[m] = rsqrt(sum_s ss_in[m][s] * ss_inv_dim + ss_eps)
+    const float* ss_in;    // [M][8] partial sums of x^2 (one per 128 columns of the 1024-wide x) or nullptr
+    float ss_inv_dim;
+    float ss_eps;
+    // producer (fp32-output GEMMs): also write the 16-bit copy of the result and its row partial sums
+    void* out16;           // [M, ld16] operand dtype or nullptr
+    int ld16;
+    float* ss_out;         // [M][8] or nullptr; slot = column / 128 (requires N == 1024)
 };
 
 constexpr int kGemmBlockM = 128;

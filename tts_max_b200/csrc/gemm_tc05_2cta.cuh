@@ -265,6 +265,17 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
             };
             if (has_res) load_res(0, res[0]);  // in flight while the mainloop finishes
+            // fused RMSNorm, consumer side: per-row 1/rms from the producer's eight partial sums
+            float rscale = 1.f;
+            if (p.ss_in != nullptr && row < p.M) {
+                const float4* sp = reinterpret_cast<const float4*>(p.ss_in + static_cast<size_t>(row) * 8);
+                const float4 s0 = sp[0], s1 = sp[1];
+                const float tot = ((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w));
+                rscale = rsqrtf(tot * p.ss_inv_dim + p.ss_eps);
+            }
+            float ssq[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ssq[i] = 0.f;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc05_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -281,7 +292,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tmem_ld_wait();
                 float v[kColsPerChunk];
 #pragma unroll
-                for (int j = 0; j < kColsPerChunk; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < kColsPerChunk; ++j) v[j] = __uint_as_float(r[j]) * rscale;
                 if (p.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
@@ -329,6 +340,15 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 o.w += res[cur][i].w;
                             }
                             *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldc + n0 + sub_w) = o;
+                            // fused RMSNorm, producer side: 16-bit copy + row sum of squares
+                            if (p.out16 != nullptr) {
+                                uint2 h2;
+                                h2.x = Half16<InT>::pack(o.x, o.y);
+                                h2.y = Half16<InT>::pack(o.z, o.w);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<InT*>(p.out16) +
+                                                          static_cast<size_t>(grow) * p.ld16 + n0 + sub_w) = h2;
+                            }
+                            ssq[i] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq[i]))));
                         } else {
                             *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldc + n0 + 2 * sub_w) = w;
                         }
@@ -339,6 +359,21 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
+            if constexpr (kOut32) {
+                if (p.ss_out != nullptr) {
+                    // 8 lanes hold the 128 columns of one row: fixed-order butterfly, one slot per warp
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float t = ssq[i];
+                        t += __shfl_xor_sync(0xffffffffu, t, 1);
+                        t += __shfl_xor_sync(0xffffffffu, t, 2);
+                        t += __shfl_xor_sync(0xffffffffu, t, 4);
+                        const int grow = row_base + i * 4 + sub_row;
+                        if ((lane & 7) == 0 && grow < p.M)
+                            p.ss_out[static_cast<size_t>(grow) * 8 + (ncol0 >> 7)] = t;
+                    }
+                }
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;

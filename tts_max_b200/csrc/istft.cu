@@ -74,17 +74,40 @@ __device__ __forceinline__ void stockham_pass(const float2 (*src)[kHalf], float2
             dst[f][j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
             dst[f][j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
         } else {
-            // direct inverse DFT-R with table twiddles exp(+2 pi i q r / R)
+            static_assert(R == 10, "only radix 4 and 10 are instantiated");
+            // inverse DFT-10 by the prime-factor map (no inner twiddles): n = (5 n1 + 2 n2) % 10,
+            // k = (5 k1 + 6 k2) % 10; two DFT-5 over n2, then five DFT-2 over n1.
+            constexpr float c1 = 0.30901699437494745f;   // cos(2 pi / 5)
+            constexpr float c2 = -0.8090169943749475f;   // cos(4 pi / 5)
+            constexpr float s1 = 0.9510565162951535f;    // sin(2 pi / 5)
+            constexpr float s2 = 0.5877852522924731f;    // sin(4 pi / 5)
+            float2 y[2][5];
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                float2 acc = v[0];
+            for (int n1 = 0; n1 < 2; ++n1) {
+                const float2 x0 = v[(5 * n1 + 0) % 10], x1 = v[(5 * n1 + 2) % 10],
+                             x2 = v[(5 * n1 + 4) % 10], x3 = v[(5 * n1 + 6) % 10],
+                             x4 = v[(5 * n1 + 8) % 10];
+                const float2 a1 = make_float2(x1.x + x4.x, x1.y + x4.y);
+                const float2 a2 = make_float2(x2.x + x3.x, x2.y + x3.y);
+                const float2 b1 = make_float2(x1.x - x4.x, x1.y - x4.y);
+                const float2 b2 = make_float2(x2.x - x3.x, x2.y - x3.y);
+                y[n1][0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
+                const float2 e1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+                const float2 e2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+                // d = i * (s * b): (re, im) -> (-im, re)
+                const float2 t1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+                const float2 t2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+                const float2 d1 = make_float2(-t1.y, t1.x);
+                const float2 d2 = make_float2(-t2.y, t2.x);
+                y[n1][1] = make_float2(e1.x + d1.x, e1.y + d1.y);
+                y[n1][4] = make_float2(e1.x - d1.x, e1.y - d1.y);
+                y[n1][2] = make_float2(e2.x + d2.x, e2.y + d2.y);
+                y[n1][3] = make_float2(e2.x - d2.x, e2.y - d2.y);
+            }
 #pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    const float2 w = tw[((q * r) % R) * (kNfft / R)];
-                    acc.x += v[r].x * w.x - v[r].y * w.y;
-                    acc.y += v[r].x * w.y + v[r].y * w.x;
-                }
-                dst[f][j0 + q * Ns] = acc;
+            for (int k2 = 0; k2 < 5; ++k2) {
+                dst[f][j0 + ((6 * k2) % 10) * Ns] = make_float2(y[0][k2].x + y[1][k2].x, y[0][k2].y + y[1][k2].y);
+                dst[f][j0 + ((5 + 6 * k2) % 10) * Ns] = make_float2(y[0][k2].x - y[1][k2].x, y[0][k2].y - y[1][k2].y);
             }
         }
     }
@@ -123,9 +146,15 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
             float2 X = make_float2(0.f, 0.f);
             if (t >= 0 && t < T) {
                 const float* row = x_pred + static_cast<size_t>(row0 + t) * ld;
-                const float mag = fminf(expf(row[k]), 100.f);
+                // exp via MUFU.EX2, sin/cos via MUFU after a two-term Cody-Waite reduction to
+                // [-pi, pi] (abs error ~5e-7, three orders below the GEMM operand rounding)
+                const float mag = fminf(__expf(row[k]), 100.f);
+                const float ph = row[kBins + k];
+                const float kq = rintf(ph * 0.15915494309189535f);
+                float rr = fmaf(kq, -6.2831854820251465f, ph);   // 2*pi (fp32 high part)
+                rr = fmaf(kq, 1.7484556000744487e-07f, rr);      // 2*pi low part: 2*pi = hi - 1.748e-7
                 float sn, cs;
-                sincosf(row[kBins + k], &sn, &cs);
+                __sincosf(rr, &sn, &cs);
                 X = make_float2(mag * cs, mag * sn);
             }
             if (k == 0) sm.buf_b[f][0].x = X.x;            // Im X[0] ignored by irfft

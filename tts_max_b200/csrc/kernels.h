@@ -44,6 +44,7 @@ int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int 
                       void* out, int ld, int out_prec, int* err_flag, cudaStream_t stream);
 
 // ---- norms.cu ----
+// w == nullptr: no elementwise weight (it is folded into the consumer GEMM's weight columns)
 int launch_rmsnorm(int prec, const float* x, const float* w, int rows, int dim, float eps,
                    void* out, cudaStream_t stream);
 int launch_layernorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
@@ -86,6 +87,13 @@ struct GemmCall {
     int ld_res;
     const uint8_t* row_valid;
     int act;
+    // RMSNorm fusion (see GemmParams); all optional
+    const float* ss_in = nullptr;
+    float ss_inv_dim = 0.f;
+    float ss_eps = 0.f;
+    void* out16 = nullptr;
+    int ld16 = 0;
+    float* ss_out = nullptr;
     // optional pre-encoded TMA descriptors (CUtensorMap, 128 B each, 64-byte aligned);
     // when null they are encoded on the fly.
     const void* tmap_a = nullptr;
@@ -93,13 +101,16 @@ struct GemmCall {
 };
 constexpr size_t kTmapBytes = 128;
 int launch_gemm(const GemmCall& c, cudaStream_t stream);
+// true when launch_gemm would pick the CTA-pair kernel (the only one with the fused-norm epilogue)
+bool gemm_uses_cta_pairs(int a_rows, int n_store);
 // encode the descriptors launch_gemm would build for `c` into tmap_a_out / tmap_b_out
 int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out);
 
 // ---- weight repack helpers (codec.cu uses them at finalize) ----
 // dst[n, tap*Cin + c] = src[n, c, tap]  (src is torch Conv1d weight [Cout, Cin, taps]), cast
+// col_scale (optional, [Cin], taps == 1): dst[n, c] = src[n, c] * col_scale[c]  (norm weight fold)
 int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const float* col_scale = nullptr);
 // in-place on fp32 c_attn weight [3*H*64, K]: rotate q,k row pairs by the head-indexed angle
 int launch_fold_rope(float* w_qkv, int heads, int head_dim, int K, const float* cos_tab,
                      const float* sin_tab, cudaStream_t stream);

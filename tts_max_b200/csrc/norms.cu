@@ -72,9 +72,13 @@ rownorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
 #pragma unroll
     for (int i = 0; i < kChunks; ++i) {
         const int c0 = i * 256 + lane * 8;
-        const float4* wp = reinterpret_cast<const float4*>(w + c0);
-        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float wv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (w != nullptr) {
+            const float4* wp = reinterpret_cast<const float4*>(w + c0);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+            wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+        }
         float o[8];
         if (kLayerNorm) {
             const float4* bp = reinterpret_cast<const float4*>(b + c0);
