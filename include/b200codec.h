@@ -125,6 +125,10 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
  * an id (and clears the flag). decode_host checks on the host instead and fails up front. */
 int b200codec_take_id_error(B200Codec* h);
 
+/* Process-wide choice of the attention kernel: 0 = tcgen05 / TMEM (default), 1 = the mma.sync
+ * flash kernel it replaced (kept for A/B measurements and as a second opinion in the tests). */
+int b200codec_set_attention_impl(int impl);
+
 /* number of kernels the library launched since creation (bench.py's gpu_launches) */
 int64_t b200codec_launch_count(const B200Codec* h);
 

@@ -35,6 +35,14 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
+int g_attention_impl = 0;  // 0 = tcgen05 (default), 1 = legacy mma.sync kernel (A/B testing)
+
+int run_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
+                  cudaStream_t s) {
+    return g_attention_impl == 1 ? launch_attention(prec, qkv, rs, heads, out, s)
+                                 : launch_attention_tc05(prec, qkv, rs, heads, out, s);
+}
+
 constexpr int kGap = 3;          // zero rows between utterances (conv7 halo)
 constexpr int kHeadLd = 1344;    // head.out columns padded to a multiple of 32 (1282 -> 1344)
 
@@ -198,8 +206,8 @@ struct PlanLayout {
     int n_utts = 0;
     int64_t toks = 0;
     int max_len = 0;
-    int64_t n_attn = 0, n_istft = 0;
-    size_t off_row_tok, off_row_utt, off_u0, off_ul, off_ut, off_attn, off_istft, off_valid;
+    int64_t n_attn = 0, n_attn128 = 0, n_istft = 0;
+    size_t off_row_tok, off_row_utt, off_u0, off_ul, off_ut, off_attn, off_attn128, off_istft, off_valid;
     size_t total_bytes = 0;
 };
 
@@ -214,6 +222,7 @@ int plan_layout(const int32_t* seqlens, int n_utts, int gap, PlanLayout* L) {
         L->toks += T;
         L->max_len = T > L->max_len ? T : L->max_len;
         L->n_attn += (T + kAttnBlockQ - 1) / kAttnBlockQ;
+        L->n_attn128 += (T + 127) / 128;
         L->n_istft += (T + kIstftOutHops - 1) / kIstftOutHops;
     }
     B200_CHECK(rows < (1 << 30), "decode: batch too large (%lld rows)", (long long)rows);
@@ -228,7 +237,8 @@ int plan_layout(const int32_t* seqlens, int n_utts, int gap, PlanLayout* L) {
     L->off_ul = 2 * R + n_utts;
     L->off_ut = 2 * R + 2 * n_utts;
     L->off_attn = (2 * R + 3 * n_utts + 3) & ~static_cast<size_t>(3);  // int4 aligned
-    L->off_istft = L->off_attn + 4 * L->n_attn;
+    L->off_attn128 = L->off_attn + 4 * L->n_attn;
+    L->off_istft = L->off_attn128 + 4 * L->n_attn128;
     L->off_valid = L->off_istft + 4 * L->n_istft;
     L->total_bytes = (L->off_valid * 4 + R + 255) & ~static_cast<size_t>(255);
     return 0;
@@ -239,7 +249,7 @@ void plan_fill(const PlanLayout& L, const int32_t* seqlens, int gap, void* host)
     uint8_t* hv = reinterpret_cast<uint8_t*>(hp + L.off_valid);
     // work items of one utterance are contiguous, which keeps its K/V in L2 while its
     // query tiles run.
-    int64_t r = 0, t0 = 0, ia = 0, ii = 0;
+    int64_t r = 0, t0 = 0, ia = 0, ia2 = 0, ii = 0;
     for (int u = 0; u < L.n_utts; ++u) {
         const int T = seqlens[u];
         hp[L.off_u0 + u] = static_cast<int32_t>(r);
@@ -252,6 +262,10 @@ void plan_fill(const PlanLayout& L, const int32_t* seqlens, int gap, void* host)
         }
         for (int q0 = 0; q0 < T; q0 += kAttnBlockQ) {
             int32_t* w = hp + L.off_attn + 4 * ia++;
+            w[0] = static_cast<int32_t>(r); w[1] = T; w[2] = q0; w[3] = 0;
+        }
+        for (int q0 = 0; q0 < T; q0 += 128) {
+            int32_t* w = hp + L.off_attn128 + 4 * ia2++;
             w[0] = static_cast<int32_t>(r); w[1] = T; w[2] = q0; w[3] = 0;
         }
         for (int b0 = 0; b0 < T; b0 += kIstftOutHops) {
@@ -282,6 +296,8 @@ void plan_bind(const PlanLayout& L, const void* dev, RowSpace* rs) {
     rs->utt_tok0 = dp + L.off_ut;
     rs->attn_work = reinterpret_cast<const int4*>(dp + L.off_attn);
     rs->n_attn_work = static_cast<int>(L.n_attn);
+    rs->attn128_work = reinterpret_cast<const int4*>(dp + L.off_attn128);
+    rs->n_attn128_work = static_cast<int>(L.n_attn128);
     rs->istft_work = reinterpret_cast<const int4*>(dp + L.off_istft);
     rs->n_istft_work = static_cast<int>(L.n_istft);
     rs->row_valid = reinterpret_cast<const uint8_t*>(dp + L.off_valid);
@@ -519,7 +535,7 @@ int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cuda
         }
         {
             Stage t(h, "attention", s);
-            RUN(launch_attention(prec, h->qkv, rs, h->H, h->y, s));
+            RUN(run_attention(prec, h->qkv, rs, h->H, h->y, s));
         }
         {
             Stage t(h, "proj_gemm", s);
@@ -900,6 +916,12 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
 
 int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0; }
 
+int b200codec_set_attention_impl(int impl) {
+    B200_CHECK(impl == 0 || impl == 1, "attention impl must be 0 (tcgen05) or 1 (mma.sync)");
+    g_attention_impl = impl;
+    return 0;
+}
+
 int b200codec_profile(B200Codec* h, int on) {
     B200_CHECK(h != nullptr, "null handle");
     h->profiling = on != 0;
@@ -1020,7 +1042,7 @@ int b200codec_attention(int precision, const void* qkv_dev, const int32_t* seqle
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TempPlan tp;
     if (tp.build(seqlens_host, n_utts, s)) return 1;
-    int rc = launch_attention(precision, qkv_dev, tp.rs, heads, out_dev, s);
+    int rc = run_attention(precision, qkv_dev, tp.rs, heads, out_dev, s);
     cudaStreamSynchronize(s);
     return rc;
 }

@@ -29,6 +29,8 @@ struct RowSpace {
     const int32_t* utt_tok0 = nullptr;   // [n] packed token offset (== sample offset / hop)
     const int4* attn_work = nullptr;     // [n_attn_work] {row0, T, q0, 0}
     int n_attn_work = 0;
+    const int4* attn128_work = nullptr;  // [n_attn128_work] {row0, T, q0, 0}, 128-query tiles
+    int n_attn128_work = 0;
     const int4* istft_work = nullptr;    // [n_istft_work] {utt, b0, 0, 0}
     int n_istft_work = 0;
 };
@@ -59,6 +61,9 @@ int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, i
 // ---- attention.cu ----
 int launch_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
                      cudaStream_t stream);
+// ---- attention_tc05.cu (tcgen05 / TMEM version; the default) ----
+int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
+                          cudaStream_t stream);
 
 // ---- istft.cu ----
 struct IstftTables {
