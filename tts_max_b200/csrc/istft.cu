@@ -236,6 +236,8 @@ int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTab
     if (!configured) {
         B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(IstftSmem))));
+        B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     istft_kernel<<<rs.n_istft_work, kIstftThreads, sizeof(IstftSmem), stream>>>(
