@@ -174,7 +174,9 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         }
         float* red_j = red + (j & 1) * 256;
         red_j[half * 128 + r] = fmaxf(mx0, mx1);
-        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+        // only the two warps that share this lane quarter exchange data: 4 independent 64-thread
+        // named barriers instead of one CTA-wide barrier per tile
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
         const float m_new = fmaxf(m_run, fmaxf(red_j[r], red_j[128 + r]));
         const float corr = ex2_approx((m_run - m_new) * c);  // first tile: ex2(-inf) = 0
         const float m_scaled = m_new * c;
@@ -250,7 +252,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     tmem_ld_wait();
     float* red_l = red + (n_kv & 1) * 256;  // the parity not used by the last tile's max exchange
     red_l[half * 128 + r] = l_run;
-    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
     if (q0 + r < T_utt) {
         const float inv = 1.f / (red_l[r] + red_l[128 + r]);
         T* dst = out + static_cast<size_t>(row0 + q0 + r) * D + head * kD + half * 32;
