@@ -138,6 +138,9 @@ struct B200Codec {
     int* err_flag_host = nullptr;  // mapped pinned
     int* err_flag_dev = nullptr;
 
+    size_t l2_persist_bytes = 0;  // persisting-L2 carve-out granted at create (0 = unsupported)
+    size_t l2_window_max = 0;
+
     int64_t launches = 0;
     bool profiling = false;
     std::vector<StageTimer> timers;
@@ -465,10 +468,14 @@ int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t 
     const RowSpace& rs = h->rs;
     double* st1 = h->gn_stats + static_cast<size_t>(stats_slot) * rs.n_utts * 64;
     double* st2 = st1 + static_cast<size_t>(rs.n_utts) * 64;
+    float2* mr_base = reinterpret_cast<float2*>(h->gn_stats + static_cast<size_t>(8) * rs.n_utts * 64);
+    float2* mr1 = mr_base + static_cast<size_t>(stats_slot) * rs.n_utts * 32;
+    float2* mr2 = mr1 + static_cast<size_t>(rs.n_utts) * 32;
     {
         Stage t(h, "groupnorm_swish", s);
         RUN(launch_groupnorm_stats(h->x, rs, C, st1, s));
-        RUN(launch_groupnorm_apply_swish(prec, h->x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, h->an, s));
+        RUN(launch_groupnorm_apply_swish(prec, h->x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, h->an, s, mr1));
+        h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
@@ -477,7 +484,8 @@ int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t 
     {
         Stage t(h, "groupnorm_swish", s);
         RUN(launch_groupnorm_stats(h->hbuf, rs, C, st2, s));
-        RUN(launch_groupnorm_apply_swish(prec, h->hbuf, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, h->an, s));
+        RUN(launch_groupnorm_apply_swish(prec, h->hbuf, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, h->an, s, mr2));
+        h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
@@ -486,7 +494,40 @@ int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t 
     return 0;
 }
 
+// The fp32 residual stream x ([rows, 1024]) is re-read by every residual epilogue and GroupNorm after
+// ~150 MB of other activations have gone through L2; pin it with a persisting access-policy window
+// on the caller's stream for the duration of the decode (restored afterwards).
+void set_l2_window(B200Codec* h, cudaStream_t s, bool on) {
+    if (h->l2_persist_bytes == 0) return;
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    if (on) {
+        size_t bytes = static_cast<size_t>(h->rs.rows) * h->C * sizeof(float);
+        if (bytes > h->l2_window_max) bytes = h->l2_window_max;
+        attr.accessPolicyWindow.base_ptr = h->x;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        const double ratio = static_cast<double>(h->l2_persist_bytes) / static_cast<double>(bytes);
+        attr.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : static_cast<float>(ratio);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+
+int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s);
+
 int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s) {
+    set_l2_window(h, s, true);
+    const int rc = forward_impl(h, ids_dev, id_type, wav_dev, s);
+    set_l2_window(h, s, false);
+    return rc;
+}
+
+int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s) {
     const int C = h->C, prec = h->cfg.precision;
     const RowSpace& rs = h->rs;
     B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * 8 * rs.n_utts * 64, s));
@@ -662,6 +703,18 @@ int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
         return 1;
     }
     *h->err_flag_host = 0;
+    // persisting L2 carve-out for the residual stream (best effort)
+    if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        size_t want = static_cast<size_t>(prop.persistingL2CacheMaxSize);
+        const size_t cap = static_cast<size_t>(prop.l2CacheSize) / 2;  // leave half of L2 to everything else
+        if (want > cap) want = cap;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            h->l2_persist_bytes = want;
+            h->l2_window_max = static_cast<size_t>(prop.accessPolicyMaxWindowSize);
+        } else {
+            cudaGetLastError();
+        }
+    }
     *out = h;
     return 0;
 }
@@ -867,7 +920,9 @@ int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
     if (prepare(h, seqlens_host, n_utts, s)) return 1;
     B200_CHECK(ids_dev && wav_dev, "decode: null device buffer");
     // 8 GroupNorm layers x [n_utts][32 groups][sum, sumsq] fp64
-    const size_t need = sizeof(double) * 8 * static_cast<size_t>(n_utts) * 64;
+    // + one float2 [n_utts][32] (mean, rstd) scratch per GroupNorm layer
+    const size_t need = sizeof(double) * 8 * static_cast<size_t>(n_utts) * 64 +
+                        sizeof(float2) * 8 * static_cast<size_t>(n_utts) * 32;
     if (h->gn_stats_bytes < need) {
         if (h->gn_stats) B200_CUDA_OK(cudaFree(h->gn_stats));
         h->gn_stats = nullptr;
@@ -1025,12 +1080,13 @@ int b200codec_groupnorm_swish(int precision, const float* x_dev, const float* ga
     if (tp.build(seqlens_host, n_utts, s)) return 1;
     double* stats = nullptr;
     const size_t bytes = sizeof(double) * 64 * static_cast<size_t>(n_utts);
-    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stats), bytes));
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stats), bytes + sizeof(float2) * 32 * n_utts));
+    float2* mean_rstd = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats) + bytes);
     int rc = 0;
     if (cudaMemsetAsync(stats, 0, bytes, s) != cudaSuccess) rc = 1;
     if (!rc) rc = launch_groupnorm_stats(x_dev, tp.rs, dim, stats, s);
     if (!rc) rc = launch_groupnorm_apply_swish(precision, x_dev, tp.rs, dim, stats, gamma_dev,
-                                               beta_dev, eps, out_dev, s);
+                                               beta_dev, eps, out_dev, s, mean_rstd);
     cudaStreamSynchronize(s);
     cudaFree(stats);
     return rc;

@@ -122,8 +122,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % num_m;
-                const int n_blk = tile / num_m;
+                // n fastest: the clusters that share one A (activation) tile run concurrently, so
+                // it is fetched from HBM once; the weight tiles are few and stay in L2
+                const int n_blk = tile % num_n;
+                const int m_blk = tile / num_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], SM::kStageBytes);
@@ -191,8 +193,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t acc_phase = 0;
         OutT* out = reinterpret_cast<OutT*>(p.out);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile % num_m;
-            const int n_blk = tile / num_m;
+            const int n_blk = tile % num_n;
+            const int m_blk = tile / num_n;
             const int row = m_blk * kGemmBlockM + q * 32 + lane;
             const bool row_ok = row < p.M;
             const bool row_zero = row_ok && p.row_valid != nullptr && p.row_valid[row] == 0;

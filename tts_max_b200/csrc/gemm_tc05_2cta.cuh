@@ -166,8 +166,10 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile % num_m;
-                const int n_blk = tile / num_m;
+                // n fastest: the clusters that share one A (activation) tile run concurrently, so
+                // it is fetched from HBM once; the weight tiles are few and stay in L2
+                const int n_blk = tile % num_n;
+                const int m_blk = tile / num_n;
                 const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
                 const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * 128;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -247,8 +249,8 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t tmem_empty_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
         const uint32_t tmem_empty_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m_blk = tile % num_m;
-            const int n_blk = tile / num_m;
+            const int n_blk = tile % num_n;
+            const int m_blk = tile / num_n;
             const int row_base = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
             const int row = row_base + lane;  // row-per-lane phase
             const bool row_zero = row < p.M && p.row_valid != nullptr && p.row_valid[row] == 0;

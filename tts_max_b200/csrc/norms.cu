@@ -155,40 +155,60 @@ groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ wor
     }
 }
 
+// (sum, sumsq) fp64 -> (mean, rstd) fp32 per (utterance, group); one warp per utterance
+__global__ void groupnorm_finalize_kernel(const double* __restrict__ stats,
+                                          const int32_t* __restrict__ utt_len, int group_size,
+                                          float eps, float2* __restrict__ mean_rstd) {
+    const int u = blockIdx.x, g = threadIdx.x;  // 32 groups
+    const double cnt = static_cast<double>(utt_len[u]) * group_size;
+    const double m = stats[(static_cast<size_t>(u) * 32 + g) * 2 + 0] / cnt;
+    double var = stats[(static_cast<size_t>(u) * 32 + g) * 2 + 1] / cnt - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mean_rstd[u * 32 + g] = make_float2(static_cast<float>(m),
+                                        static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+
+// y = swish((x - mean) * rstd * gamma + beta) -> operand dtype; halo rows are written as zeros
+// (the conv that follows reads them as its padding). 128 threads per row, 8 channels per thread:
+// 2 x 128-bit loads, one 128-bit store; a 256-thread CTA streams two rows per iteration.
 template <typename OutT>
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
-                             const int32_t* __restrict__ utt_len, int rows, int dim,
-                             const double* __restrict__ stats, const float* __restrict__ gamma,
-                             const float* __restrict__ beta, float eps, OutT* __restrict__ out) {
-    const int group = threadIdx.x >> 3;
-    const int c0 = threadIdx.x * 4;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c0));
-    int cur = -1;
-    float mean = 0.f, rstd = 0.f;
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+                             int rows, int dim, const float2* __restrict__ mean_rstd,
+                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                             OutT* __restrict__ out) {
+    const int t = threadIdx.x & 127;
+    const int sub = threadIdx.x >> 7;  // which of the two rows of an iteration
+    const int c0 = t * 8;
+    const int group = t >> 2;          // 32 channels per group = 4 threads
+    float g[8], b[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    }
+    for (int r = blockIdx.x * 2 + sub; r < rows; r += gridDim.x * 2) {
         const int u = row_utt[r];
-        uint2 packed = make_uint2(0u, 0u);  // halo rows: zeros (conv padding)
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
         if (u >= 0) {
-            if (u != cur) {
-                cur = u;
-                const double cnt = static_cast<double>(utt_len[u]) * (dim / 32);
-                const double m = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 0] / cnt;
-                double var = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 1] / cnt - m * m;
-                var = var < 0.0 ? 0.0 : var;
-                mean = static_cast<float>(m);
-                rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-            }
-            const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * dim + c0);
-            float y[4] = {(v.x - mean) * rstd * g.x + bt.x, (v.y - mean) * rstd * g.y + bt.y,
-                          (v.z - mean) * rstd * g.z + bt.z, (v.w - mean) * rstd * g.w + bt.w};
+            const float2 mr = __ldg(mean_rstd + u * 32 + group);
+            const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * dim + c0);
+            const float4 v0 = xp[0], v1 = xp[1];
+            float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = y[j] / (1.f + expf(-y[j]));  // x * sigmoid(x)
+            for (int j = 0; j < 8; ++j) {
+                const float n = (y[j] - mr.x) * mr.y * g[j] + b[j];
+                y[j] = __fdividef(n, 1.f + __expf(-n));  // x * sigmoid(x)
+            }
             packed.x = Half16<OutT>::pack(y[0], y[1]);
             packed.y = Half16<OutT>::pack(y[2], y[3]);
+            packed.z = Half16<OutT>::pack(y[4], y[5]);
+            packed.w = Half16<OutT>::pack(y[6], y[7]);
         }
-        *reinterpret_cast<uint2*>(out + static_cast<size_t>(r) * dim + c0) = packed;
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * dim + c0) = packed;
     }
 }
 
@@ -217,18 +237,19 @@ int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* 
 
 int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, int dim,
                                  const double* stats, const float* gamma, const float* beta,
-                                 float eps, void* out, cudaStream_t stream) {
+                                 float eps, void* out, cudaStream_t stream, float2* mean_rstd) {
     B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
     if (rs.rows <= 0) return 0;
-    int grid = rs.rows < kNumSMs * 8 ? rs.rows : kNumSMs * 8;
+    groupnorm_finalize_kernel<<<rs.n_utts, 32, 0, stream>>>(stats, rs.utt_len, dim / 32, eps, mean_rstd);
+    B200_CUDA_OK(cudaGetLastError());
+    int grid = (rs.rows + 1) / 2;
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     if (prec == kPrecBf16)
         groupnorm_apply_swish_kernel<__nv_bfloat16><<<grid, kGnThreads, 0, stream>>>(
-            x, rs.row_utt, rs.utt_len, rs.rows, dim, stats, gamma, beta, eps,
-            static_cast<__nv_bfloat16*>(out));
+            x, rs.row_utt, rs.rows, dim, mean_rstd, gamma, beta, static_cast<__nv_bfloat16*>(out));
     else if (prec == kPrecFp16)
         groupnorm_apply_swish_kernel<__half><<<grid, kGnThreads, 0, stream>>>(
-            x, rs.row_utt, rs.utt_len, rs.rows, dim, stats, gamma, beta, eps,
-            static_cast<__half*>(out));
+            x, rs.row_utt, rs.rows, dim, mean_rstd, gamma, beta, static_cast<__half*>(out));
     else {
         set_error("groupnorm: unsupported precision %d", prec);
         return 1;
