@@ -37,6 +37,9 @@ WORKLOADS = {
     "c4": ("4 clips x 60 s long-form (BASELINE config 4)", 4, 3000),
     "c5": ("64 windows x (100 context + 50 new) tokens (BASELINE config 5)", 64, 150),
 }
+# BASELINE config 3: 10 000 utterances of 2-20 s (100..1000 tokens, seed 2024), length-bucketed varlen
+# packs of <= 16 384 tokens, sharded over the ranks by cost (strong scaling: total work is fixed).
+C3_UTTS, C3_SEED, C3_BUCKET_TOKENS = 10_000, 2024, 16_384
 
 LINEAR_FLOPS_PER_TOKEN = 373_854_208  # SURVEY.md 8a / BASELINE.md 4
 GEMM_FLOPS_PER_TOKEN = 4_194_304 + 14_680_064 + 50_331_648 + 301_989_888 + 2_625_536  # tcgen05 GEMM/conv kernel
@@ -143,7 +146,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    desc, n_utts, tokens = WORKLOADS[args.workload]
+    desc, n_utts, tokens = WORKLOADS["c2" if args.workload == "c3" else args.workload]
     clips = min(2, n_utts)  # bounded sample of the workload: `clips` of its utterances per step
     value, ms, cores = cpu_decode_rate(tokens, clips, args.steps, max(args.warmup, 1))
     sample = f"{clips} of the {n_utts} x {tokens}-token utterances per step (same ids seed), oracle port of the reference algorithm, fp32"
@@ -162,11 +165,99 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+def run_c3(args):
+    """Strong-scaling run of BASELINE config 3; one step = the rank's whole shard decoded once."""
+    import torch
+    import torch.distributed as dist
+
+    from tts_max_b200 import sharding
+    from tts_max_b200.codec import decoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator().manual_seed(C3_SEED)
+    n_utts = args.c3_utts
+    lengths = torch.randint(100, 1001, (n_utts,), generator=g).tolist()
+    mine = sharding.partition_utterances(lengths, world)[rank]
+    buckets = sharding.bucket_by_length(mine, lengths, max_tokens=C3_BUCKET_TOKENS)
+    dec = decoder.Decoder(16000, HOP, None, None, precision=args.precision, init_seed=0).to(dev).eval()
+    gi = torch.Generator().manual_seed(1234 + rank)
+    packs = []
+    for b in buckets:
+        seqlens = [lengths[i] for i in b]
+        packs.append((torch.randint(0, 65536, (sum(seqlens),), generator=gi, dtype=torch.int64).to(dev), seqlens))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_pass():
+        out = None
+        for ids, seqlens in packs:
+            out = dec.decode_packed_device(ids, seqlens)
+        return out
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        one_pass()
+    barrier()
+    launches0 = dec.launch_count()
+    steps = max(1, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        time.sleep(0.15)
+        e0.record()
+        for _ in range(steps):
+            wav = one_pass()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = dec.launch_count() - launches0
+    assert torch.isfinite(wav[:4096]).all()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_audio_s = sum(lengths) / TOKEN_RATE
+    if rank == 0:
+        ms_per_step = ms / steps
+        flops = sum(sharding.utterance_cost(t) for t in lengths)
+        peak = read_peaks()["tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": round(total_audio_s / (ms_per_step / 1e3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(ms_per_step, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"c3: {n_utts} utterances of 2-20 s (BASELINE config 3), length-bucketed varlen packs of <= "
+                                   f"{C3_BUCKET_TOKENS} tokens, LPT-sharded over {world} rank(s)",
+                       "audio_seconds_total": total_audio_s, "packs_on_rank0": len(packs),
+                       "parallelism": f"dp{world} (independent utterances, no data-path collective)",
+                       "l2": "each pack's working set (weights 374 MB + ~0.6 GB activations) exceeds the 126 MB L2",
+                       "timing": "CUDA events around the rank's whole shard, max over ranks"},
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "roofline": {"kernel": "whole step (all kernels)", "bound": "tensor", "achieved": round(flops / (ms_per_step / 1e3) / 1e12 / world, 1),
+                         "peak": peak, "unit": "TFLOP/s per GPU", "frac": round(flops / (ms_per_step / 1e3) / 1e12 / world / peak, 4), "traffic": None},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from tts_max_b200.codec import decoder
+
+    if args.workload == "c3":
+        return run_c3(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -309,7 +400,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3"])
+    ap.add_argument("--c3-utts", type=int, default=C3_UTTS)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
