@@ -350,10 +350,15 @@ def run_ours(args):
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["tflops_sustained"]
         step_flops = (LINEAR_FLOPS_PER_TOKEN + ATTN_FLOPS_PER_TOKEN_PER_T * tokens) * total_tokens
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01b_gemm_traffic.json")
+        if os.path.exists(tpath) and args.workload == "c2":
+            with open(tpath) as f:
+                traffic = json.load(f)["mean_dram_bytes_per_launch"]  # bytes per launch, from the ncu capture
         roofline = {
-            "kernel": "gemm_tc05_kernel (tcgen05 GEMM / implicit conv1d; all dense layers)",
+            "kernel": "gemm_tc05_2cta_kernel (tcgen05 cta_group::2 GEMM / implicit conv1d; all dense layers)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
+            "frac": round(achieved / peak, 4), "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
             "launches_per_step": n_gemm, "avg_launch_ms": round(gemm_ms / n_gemm, 4),
             "flops_per_step": gemm_flops,
@@ -361,6 +366,29 @@ def run_ours(args):
             "whole_step": {"flops": step_flops, "achieved": round(step_flops / (ms_per_step / 1e3) / 1e12, 1),
                            "frac": round(step_flops / (ms_per_step / 1e3) / 1e12 / peak, 4)},
         }
+        # HBM-bound kernels: algorithmic bytes per token (operand dtype as stored) / stage time
+        rows = total_tokens + 3 * (n_utts - 1)
+        hbm = peaks["hbm_gbs"]
+
+        def hbm_entry(name, stage, bytes_per_row, launches):
+            ms = stage_ms.get(stage, 0.0)
+            gbs = bytes_per_row * rows * launches / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+            return {"kernel": name, "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
+                    "frac": round(gbs / hbm, 4), "ms_per_step": round(ms, 4), "launches_per_step": launches}
+
+        roofline["hbm_kernels"] = [
+            hbm_entry("fsq_lookup_kernel (8 B id in, 2048 x 2 B out)", "fsq_lookup", 8 + 4096, 1),
+            hbm_entry("groupnorm stats + finalize + apply_swish (2 x 4096 B in, 2048 B out)", "groupnorm_swish", 2 * 4096 + 2048, 8),
+            hbm_entry("rownorm_kernel / LayerNorm (4096 B in, 2048 B out)", "layernorm", 4096 + 2048, 1),
+            hbm_entry("istft_kernel (1282 x 4 B in, 320 x 4 B out; instruction-bound in practice)", "istft", 5128 + 1280, 1),
+        ]
+        attn_ms = stage_ms.get("attention", 0.0)
+        if attn_ms > 0:
+            attn_flops = ATTN_FLOPS_PER_TOKEN_PER_T * tokens * total_tokens
+            roofline["attention"] = {
+                "kernel": "attention_tc05_kernel (tcgen05, S/P/O in TMEM)", "bound": "MUFU (16 384 exp per 128x128 tile: half the tensor roofline for d = 64)",
+                "achieved": round(attn_flops / (attn_ms / 1e3) / 1e12, 1), "peak": peak / 2, "unit": "TFLOP/s",
+                "frac": round(attn_flops / (attn_ms / 1e3) / 1e12 / (peak / 2), 4), "ms_per_step": round(attn_ms, 4)}
         if not args.no_cpu_baseline:
             clips = min(2, n_utts)
             v, ms, cores = cpu_decode_rate(tokens, clips, steps=3, warmup=1)

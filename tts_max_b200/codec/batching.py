@@ -1,0 +1,116 @@
+"""Caller-side batching for the decode path.
+
+The reference's two high-volume consumers of `AudioDecoder.decode` feed it one utterance at a time:
+  * RLHF rewards: `RewardFunc._decode_audio` (tts/training/rlhf/rewards.py:67-98) concatenates prompt
+    and generated ids, decodes, and strips the prompt's samples -- in a Python loop over
+    `num_generations x batch` completions;
+  * dataset tooling: codes live on disk as one flat int32 array plus an offsets array
+    (`{split}_codes.npy` / `{split}_codes_index.npy`, tools/data/data_vectorizer.py:122-146, read back
+    by tts/data/data_utils.py:98-152), which already IS a packed varlen layout.
+Both map onto one varlen launch sequence per bucket of <= max_tokens tokens; every waveform equals the
+single-utterance `decode` of the same ids.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Iterable, Iterator, Sequence
+
+import numpy as np
+import torch
+
+from tts_max_b200 import sharding
+from tts_max_b200.codec.decoding import AudioDecoder
+
+
+def extract_speech_ids(speech_tokens_str: Sequence[str]) -> list[int]:
+    """`<|s_N|>` strings -> N (mirror of tts/inference/inferencing.py:53-63; unexpected tokens are
+    skipped there with an error log, and skipped here)."""
+    speech_ids = []
+    for token_str in speech_tokens_str:
+        if token_str.startswith("<|s_") and token_str.endswith("|>"):
+            speech_ids.append(int(token_str[4:-2]))
+    return speech_ids
+
+
+def decode_completions(
+    audio_decoder: AudioDecoder,
+    prompt_speech_ids: Sequence[torch.Tensor],
+    generated_speech_ids: Sequence[torch.Tensor],
+    max_tokens: int = 16384,
+) -> list[torch.Tensor]:
+    """Batched `RewardFunc._decode_audio`: for every (prompt, completion) pair decode
+    `cat([prompt, completion])` and drop the first `int(len(prompt) / token_rate * sample_rate)` samples
+    (rewards.py:84-93). An empty completion yields `zeros((1, 0))` like rewards.py:76-82. Results are
+    float32 CPU tensors of shape (1, L), in input order."""
+    if len(prompt_speech_ids) != len(generated_speech_ids):
+        raise ValueError("prompt_speech_ids and generated_speech_ids must have the same length")
+    out: list[torch.Tensor | None] = [None] * len(generated_speech_ids)
+    todo, utts = [], []
+    for i, (p, g) in enumerate(zip(prompt_speech_ids, generated_speech_ids)):
+        if g.numel() == 0:
+            out[i] = torch.zeros((1, 0))
+            continue
+        todo.append(i)
+        utts.append(torch.cat([p.detach().to("cpu", torch.int64).reshape(-1), g.detach().to("cpu", torch.int64).reshape(-1)]))
+    lengths = [int(u.numel()) for u in utts]
+    for bucket in sharding.bucket_by_length(range(len(utts)), lengths, max_tokens=max_tokens):
+        wavs = audio_decoder.decode_batch([utts[k] for k in bucket])
+        for k, wav in zip(bucket, wavs):
+            i = todo[k]
+            prompt_wav_length = int(prompt_speech_ids[i].numel() / audio_decoder.token_rate * audio_decoder.sample_rate)
+            out[i] = wav[:, prompt_wav_length:]
+    return out  # type: ignore[return-value]
+
+
+class CodeStore:
+    """Read-only view of the vectorizer's on-disk codes: flat int32 `codes` (memmap) + `index` offsets."""
+
+    def __init__(self, codes: np.ndarray, index: np.ndarray):
+        if codes.dtype != np.int32 or codes.ndim != 1:
+            raise ValueError("codes must be a flat int32 array")
+        self.codes = codes
+        self.index = np.asarray(index, dtype=np.int64)
+
+    @staticmethod
+    def open(dataset_dir: str, split: str) -> "CodeStore":
+        """`{split}_codes.npy` is a raw int32 memmap (no .npy header), `{split}_codes_index.npy` a real
+        .npy file -- exactly as tools/data/data_vectorizer.py:122-146 writes them."""
+        codes = np.memmap(os.path.join(dataset_dir, f"{split}_codes.npy"), dtype=np.int32, mode="r")
+        index = np.load(os.path.join(dataset_dir, f"{split}_codes_index.npy"))
+        return CodeStore(codes, index)
+
+    def __len__(self) -> int:
+        return int(self.index.shape[0])
+
+    def span(self, i: int) -> tuple[int, int]:
+        """[left, right) of sample i (tts/data/data_utils.py:143-147)."""
+        left = int(self.index[i])
+        right = int(self.index[i + 1]) if i < len(self.index) - 1 else int(self.codes.shape[0])
+        return left, right
+
+    def length(self, i: int) -> int:
+        left, right = self.span(i)
+        return right - left
+
+
+def decode_code_store(
+    audio_decoder: AudioDecoder, store: CodeStore, sample_ids: Iterable[int] | None = None, max_tokens: int = 16384
+) -> Iterator[tuple[int, torch.Tensor]]:
+    """Decodes samples of a CodeStore in length-sorted varlen buckets; yields (sample id, (1, L) float32
+    CPU waveform). The int32 codes go to the GPU as stored (no int64 widening)."""
+    ids = list(range(len(store))) if sample_ids is None else [int(i) for i in sample_ids]
+    lengths = {i: store.length(i) for i in ids}
+    for i in ids:
+        if lengths[i] <= 0:
+            raise ValueError(f"sample {i} has no codes")
+    dec = audio_decoder._decoder
+    hop = dec.hop_length
+    for bucket in sharding.bucket_by_length(ids, lengths, max_tokens=max_tokens):
+        seqlens = [lengths[i] for i in bucket]
+        packed = np.concatenate([store.codes[slice(*store.span(i))] for i in bucket]).astype(np.int32, copy=False)
+        wav = dec.decode_packed_host(torch.from_numpy(np.ascontiguousarray(packed)), seqlens)
+        off = 0
+        for i, n in zip(bucket, seqlens):
+            yield i, wav[off * hop:(off + n) * hop].view(1, -1)
+            off += n

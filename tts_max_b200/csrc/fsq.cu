@@ -58,8 +58,7 @@ fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_t
                   const float* __restrict__ w_out, const float* __restrict__ b_out, int channels,
                   OutT* __restrict__ out, int ld, int* __restrict__ err_flag) {
     // channel block handled by this thread (grid.y covers channels > 2048 if ever needed)
-    const int c0 = (blockIdx.y * kFsqThreads + threadIdx.x) * kFsqChanPerThread;
-    if (c0 >= channels) return;
+    const int c0 = (blockIdx.y * kFsqThreads + threadIdx.x) * kFsqChanPerThread;  // < channels (checked by the launcher)
 
     float w[kFsqChanPerThread][8];
     float b[kFsqChanPerThread];
@@ -73,23 +72,38 @@ fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_t
     }
 
     // each CTA owns a contiguous slab of rows, so the 72 KB weight block it holds in registers is
-    // fetched once per kFsqRowsPerBlock rows instead of once per handful of rows
+    // fetched once per kFsqRowsPerBlock rows. The slab's ids are gathered into shared memory first:
+    // the row -> token -> id chain is two dependent global loads, which must not sit inside the
+    // serial row loop.
+    __shared__ int s_id[kFsqRowsPerBlock];  // -1: halo row, otherwise the 16-bit code id
     const int r_begin = blockIdx.x * kFsqRowsPerBlock;
     const int r_end = min(r_begin + kFsqRowsPerBlock, rows);
-#pragma unroll 2
+    if (threadIdx.x < kFsqRowsPerBlock) {
+        const int r = r_begin + threadIdx.x;
+        int v = -1;
+        if (r < r_end) {
+            const int tok = row_tok ? row_tok[r] : r;
+            if (tok >= 0) {
+                const long long id = static_cast<long long>(ids[tok]);
+                if (id < 0 || id > 65535) {
+                    if (blockIdx.y == 0) atomicExch(err_flag, 1);
+                }
+                v = static_cast<int>(static_cast<unsigned>(id) & 0xFFFFu);
+            }
+        }
+        s_id[threadIdx.x] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
     for (int r = r_begin; r < r_end; ++r) {
-        const int tok = row_tok ? row_tok[r] : r;
+        const int sid = s_id[r - r_begin];
         float v[kFsqChanPerThread];
-        if (tok < 0) {
+        if (sid < 0) {
             // halo row of the padded row space: conv operands must see zeros here
 #pragma unroll
             for (int i = 0; i < kFsqChanPerThread; ++i) v[i] = 0.f;
         } else {
-            const long long id = static_cast<long long>(ids[tok]);
-            if (id < 0 || id > 65535) {
-                if (threadIdx.x == 0 && blockIdx.y == 0) atomicExch(err_flag, 1);
-            }
-            const unsigned uid = static_cast<unsigned>(id) & 0xFFFFu;
+            const unsigned uid = static_cast<unsigned>(sid);
             float code[8];
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
@@ -133,7 +147,8 @@ int launch_typed(const void* ids, int id_type, const int32_t* row_tok, int rows,
 int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int rows,
                       const float* w_out, const float* b_out, int channels, void* out, int ld,
                       int out_prec, int* err_flag, cudaStream_t stream) {
-    B200_CHECK(channels % kFsqChanPerThread == 0, "fsq: channels must be a multiple of 8");
+    B200_CHECK(channels % (kFsqChanPerThread * kFsqThreads) == 0, "fsq: channels must be a multiple of %d",
+               kFsqChanPerThread * kFsqThreads);
     if (out_prec < 0)
         return launch_typed<float>(ids, id_type, row_tok, rows, w_out, b_out, channels, out, ld,
                                    err_flag, stream);
