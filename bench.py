@@ -256,6 +256,9 @@ def run_ours(args):
 
     from tts_max_b200.codec import decoder
 
+    if args.no_pdl:
+        from tts_max_b200 import _lib
+        _lib.check(_lib.load().b200codec_set_pdl(0))
     if args.workload == "c3":
         return run_c3(args)
 
@@ -432,6 +435,7 @@ def main():
     ap.add_argument("--c3-utts", type=int, default=C3_UTTS)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B: plain stream-ordered launches instead of programmatic dependent launch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

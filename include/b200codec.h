@@ -129,6 +129,10 @@ int b200codec_take_id_error(B200Codec* h);
  * flash kernel it replaced (kept for A/B measurements and as a second opinion in the tests). */
 int b200codec_set_attention_impl(int impl);
 
+/* Process-wide: launch the kernel chain with programmatic dependent launch (1, default) or as
+ * plain stream-ordered launches (0; for A/B measurements). */
+int b200codec_set_pdl(int on);
+
 /* number of kernels the library launched since creation (bench.py's gpu_launches) */
 int64_t b200codec_launch_count(const B200Codec* h);
 

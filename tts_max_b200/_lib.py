@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200codec_decode_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_take_id_error": (c_int, [c_void_p]),
     "b200codec_set_attention_impl": (c_int, [c_int]),
+    "b200codec_set_pdl": (c_int, [c_int]),
     "b200codec_launch_count": (c_int64, [c_void_p]),
     "b200codec_profile": (c_int, [c_void_p, c_int]),
     "b200codec_stage_times": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),

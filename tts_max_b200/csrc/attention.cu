@@ -95,6 +95,8 @@ template <typename T>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, const int4* __restrict__ work,
                  int heads) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(128) uint8_t smem[(1 + 2 + 2) * 64 * 64 * 2];  // Q, K[2], V[2] = 40 KB
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sK = sQ + 8192;
@@ -268,12 +270,12 @@ int launch_attention(int prec, const void* qkv, const RowSpace& rs, int heads, v
     if (rs.n_attn_work <= 0) return 0;
     dim3 grid(rs.n_attn_work, heads);
     if (prec == kPrecBf16)
-        attention_kernel<__nv_bfloat16><<<grid, kAttnThreads, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), rs.attn_work,
-            heads);
+        B200_CUDA_OK(launch_kernel(attention_kernel<__nv_bfloat16>, grid, dim3(kAttnThreads), 0, stream,
+                                   static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+                                   rs.attn_work, heads));
     else if (prec == kPrecFp16)
-        attention_kernel<__half><<<grid, kAttnThreads, 0, stream>>>(
-            static_cast<const __half*>(qkv), static_cast<__half*>(out), rs.attn_work, heads);
+        B200_CUDA_OK(launch_kernel(attention_kernel<__half>, grid, dim3(kAttnThreads), 0, stream,
+                                   static_cast<const __half*>(qkv), static_cast<__half*>(out), rs.attn_work, heads));
     else {
         set_error("attention: unsupported precision %d", prec);
         return 1;

@@ -81,6 +81,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 8);
     float* red = reinterpret_cast<float*>(smem + AttnSmem::kRed);  // [2 parities][2 halves][128 rows]
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int half = warp >> 2;               // which 64 keys of a tile / which 32 output columns
@@ -107,6 +108,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     tc05_fence_before();
     __syncthreads();
     tc05_fence_after();
+    pdl_wait();  // prologue above overlaps the predecessor's tail; no global access before this point
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tmem_s = tmem_base + lane_addr + half * 64;        // this thread's 64 score columns
@@ -299,11 +301,11 @@ int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int hea
         configured = true;
     }
     if (prec == kPrecBf16)
-        attention_tc05_kernel<__nv_bfloat16><<<grid, kThreads, AttnSmem::kTotal, stream>>>(
-            tm, static_cast<__nv_bfloat16*>(out), rs.attn128_work, heads);
+        B200_CUDA_OK(launch_kernel(attention_tc05_kernel<__nv_bfloat16>, grid, dim3(kThreads), AttnSmem::kTotal, stream,
+                                   tm, static_cast<__nv_bfloat16*>(out), rs.attn128_work, heads));
     else
-        attention_tc05_kernel<__half><<<grid, kThreads, AttnSmem::kTotal, stream>>>(
-            tm, static_cast<__half*>(out), rs.attn128_work, heads);
+        B200_CUDA_OK(launch_kernel(attention_tc05_kernel<__half>, grid, dim3(kThreads), AttnSmem::kTotal, stream, tm,
+                                   static_cast<__half*>(out), rs.attn128_work, heads));
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

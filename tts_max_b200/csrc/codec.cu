@@ -24,6 +24,8 @@
 
 namespace b200 {
 
+int g_use_pdl = 1;
+
 static thread_local char g_err[1024] = {0};
 
 void set_error(const char* fmt, ...) {
@@ -974,6 +976,11 @@ int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0;
 int b200codec_set_attention_impl(int impl) {
     B200_CHECK(impl == 0 || impl == 1, "attention impl must be 0 (tcgen05) or 1 (mma.sync)");
     g_attention_impl = impl;
+    return 0;
+}
+
+int b200codec_set_pdl(int on) {
+    g_use_pdl = on != 0;
     return 0;
 }
 

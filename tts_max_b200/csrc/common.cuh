@@ -41,6 +41,38 @@ void set_error(const char* fmt, ...);
 constexpr int kNumSMs = 148;
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+// ---------------------------------------------------------------------------
+// Every kernel of the decode chain is launched with programmatic stream serialization: a kernel
+// may be scheduled while its predecessor is still draining, runs its prologue (barrier init, TMEM
+// allocation, descriptor prefetch), and blocks in pdl_wait() before its first global access.
+// ~12 us of fixed cost per GEMM launch x 59 launches was ~19 % of a config-2 step.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+extern int g_use_pdl;  // codec.cu; 1 = on (default)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(kFsqThreads)
 fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_tok, int rows,
                   const float* __restrict__ w_out, const float* __restrict__ b_out, int channels,
                   OutT* __restrict__ out, int ld, int* __restrict__ err_flag) {
+    pdl_launch_dependents();
+    pdl_wait();
     // channel block handled by this thread (grid.y covers channels > 2048 if ever needed)
     const int c0 = (blockIdx.y * kFsqThreads + threadIdx.x) * kFsqChanPerThread;  // < channels (checked by the launcher)
 
@@ -131,13 +133,13 @@ int launch_typed(const void* ids, int id_type, const int32_t* row_tok, int rows,
                             (kFsqThreads * kFsqChanPerThread);
     dim3 grid((rows + kFsqRowsPerBlock - 1) / kFsqRowsPerBlock, chan_blocks);
     if (id_type == 1)
-        fsq_lookup_kernel<OutT, long long><<<grid, kFsqThreads, 0, stream>>>(
-            static_cast<const long long*>(ids), row_tok, rows, w_out, b_out, channels,
-            static_cast<OutT*>(out), ld, err_flag);
+        B200_CUDA_OK(launch_kernel(fsq_lookup_kernel<OutT, long long>, grid, dim3(kFsqThreads), 0, stream,
+                                   static_cast<const long long*>(ids), row_tok, rows, w_out, b_out, channels,
+                                   static_cast<OutT*>(out), ld, err_flag));
     else
-        fsq_lookup_kernel<OutT, int><<<grid, kFsqThreads, 0, stream>>>(
-            static_cast<const int*>(ids), row_tok, rows, w_out, b_out, channels,
-            static_cast<OutT*>(out), ld, err_flag);
+        B200_CUDA_OK(launch_kernel(fsq_lookup_kernel<OutT, int>, grid, dim3(kFsqThreads), 0, stream,
+                                   static_cast<const int*>(ids), row_tok, rows, w_out, b_out, channels,
+                                   static_cast<OutT*>(out), ld, err_flag));
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

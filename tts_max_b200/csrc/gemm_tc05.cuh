@@ -87,6 +87,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -114,6 +115,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc05_fence_before();
     __syncthreads();
     tc05_fence_after();
+    pdl_wait();  // everything above overlaps the predecessor's tail
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -305,8 +307,7 @@ int launch_gemm_tc05(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     int grid = num_m * num_n;
     if (grid > kNumSMs) grid = kNumSMs;
     if (grid < 1) return 0;
-    kern<<<grid, kGemmThreads, SM::kTotal, stream>>>(ta, tb, p);
-    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), SM::kTotal, stream, ta, tb, p));
     return 0;
 }
 

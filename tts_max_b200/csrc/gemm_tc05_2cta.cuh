@@ -127,6 +127,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -158,6 +159,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc05_fence_before();
     cluster_sync_all();  // peer barriers initialised, TMEM allocated in both CTAs
     tc05_fence_after();
+    pdl_wait();  // barrier init, TMEM allocation and the cluster sync overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -405,8 +407,7 @@ int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     int clusters = num_m * num_n;
     if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
     if (clusters < 1) return 0;
-    kern<<<2 * clusters, kGemm2Threads, Gemm2Smem::kTotal, stream>>>(ta, tb, p);
-    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2Smem::kTotal, stream, ta, tb, p));
     return 0;
 }
 

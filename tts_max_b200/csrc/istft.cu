@@ -118,6 +118,8 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
              const int32_t* __restrict__ utt_row0, const int32_t* __restrict__ utt_len,
              const int32_t* __restrict__ utt_tok0, const float2* __restrict__ twiddle,
              const float* __restrict__ window, float* __restrict__ wav) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
 
@@ -240,9 +242,9 @@ int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTab
                                           cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    istft_kernel<<<rs.n_istft_work, kIstftThreads, sizeof(IstftSmem), stream>>>(
-        x_pred, ld, rs.istft_work, rs.utt_row0, rs.utt_len, rs.utt_tok0, tab.twiddle, tab.window,
-        wav);
+    B200_CUDA_OK(launch_kernel(istft_kernel, dim3(rs.n_istft_work), dim3(kIstftThreads), sizeof(IstftSmem), stream,
+                               x_pred, ld, rs.istft_work, rs.utt_row0, rs.utt_len, rs.utt_tok0, tab.twiddle,
+                               tab.window, wav));
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -36,6 +36,8 @@ template <typename OutT, int kChunks, bool kLayerNorm>
 __global__ void __launch_bounds__(kNormWarps * 32)
 rownorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                const float* __restrict__ b, int rows, float eps, OutT* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int dim = kChunks * 256;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kNormWarps + (threadIdx.x >> 5);
@@ -101,11 +103,11 @@ int launch_rownorm(int prec, const float* x, const float* w, const float* b, int
     if (rows <= 0) return 0;
     const int grid = (rows + kNormWarps - 1) / kNormWarps;
     if (prec == kPrecBf16)
-        rownorm_kernel<__nv_bfloat16, 4, kLayerNorm><<<grid, kNormWarps * 32, 0, stream>>>(
-            x, w, b, rows, eps, static_cast<__nv_bfloat16*>(out));
+        B200_CUDA_OK(launch_kernel(rownorm_kernel<__nv_bfloat16, 4, kLayerNorm>, dim3(grid), dim3(kNormWarps * 32), 0,
+                                   stream, x, w, b, rows, eps, static_cast<__nv_bfloat16*>(out)));
     else if (prec == kPrecFp16)
-        rownorm_kernel<__half, 4, kLayerNorm><<<grid, kNormWarps * 32, 0, stream>>>(
-            x, w, b, rows, eps, static_cast<__half*>(out));
+        B200_CUDA_OK(launch_kernel(rownorm_kernel<__half, 4, kLayerNorm>, dim3(grid), dim3(kNormWarps * 32), 0, stream,
+                                   x, w, b, rows, eps, static_cast<__half*>(out)));
     else {
         set_error("row norm: unsupported precision %d", prec);
         return 1;
@@ -127,6 +129,8 @@ constexpr int kGnRowsPerBlock = 16;
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ work, int dim,
                        double* __restrict__ stats, const int32_t* __restrict__ row_utt) {
+    pdl_launch_dependents();
+    pdl_wait();
     // dim == 1024: 32 channels per group == 8 consecutive threads
     const int4 wk = work[blockIdx.x];
     const int t0 = wk.z + blockIdx.y * kGnRowsPerBlock;
@@ -159,6 +163,8 @@ groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ wor
 __global__ void groupnorm_finalize_kernel(const double* __restrict__ stats,
                                           const int32_t* __restrict__ utt_len, int group_size,
                                           float eps, float2* __restrict__ mean_rstd) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int u = blockIdx.x, g = threadIdx.x;  // 32 groups
     const double cnt = static_cast<double>(utt_len[u]) * group_size;
     const double m = stats[(static_cast<size_t>(u) * 32 + g) * 2 + 0] / cnt;
@@ -177,6 +183,8 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
                              int rows, int dim, const float2* __restrict__ mean_rstd,
                              const float* __restrict__ gamma, const float* __restrict__ beta,
                              OutT* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = threadIdx.x & 127;
     const int sub = threadIdx.x >> 7;  // which of the two rows of an iteration
     const int c0 = t * 8;
@@ -230,7 +238,8 @@ int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* 
     if (rs.n_attn_work <= 0) return 0;
     static_assert(kAttnBlockQ % kGnRowsPerBlock == 0, "GroupNorm chunks must tile the work item");
     dim3 grid(rs.n_attn_work, kAttnBlockQ / kGnRowsPerBlock);
-    groupnorm_stats_kernel<<<grid, kGnThreads, 0, stream>>>(x, rs.attn_work, dim, stats, rs.row_utt);
+    B200_CUDA_OK(launch_kernel(groupnorm_stats_kernel, grid, dim3(kGnThreads), 0, stream, x, rs.attn_work, dim, stats,
+                               rs.row_utt));
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -240,16 +249,19 @@ int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, i
                                  float eps, void* out, cudaStream_t stream, float2* mean_rstd) {
     B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
     if (rs.rows <= 0) return 0;
-    groupnorm_finalize_kernel<<<rs.n_utts, 32, 0, stream>>>(stats, rs.utt_len, dim / 32, eps, mean_rstd);
+    B200_CUDA_OK(launch_kernel(groupnorm_finalize_kernel, dim3(rs.n_utts), dim3(32), 0, stream, stats, rs.utt_len,
+                               dim / 32, eps, mean_rstd));
     B200_CUDA_OK(cudaGetLastError());
     int grid = (rs.rows + 1) / 2;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     if (prec == kPrecBf16)
-        groupnorm_apply_swish_kernel<__nv_bfloat16><<<grid, kGnThreads, 0, stream>>>(
-            x, rs.row_utt, rs.rows, dim, mean_rstd, gamma, beta, static_cast<__nv_bfloat16*>(out));
+        B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__nv_bfloat16>, dim3(grid), dim3(kGnThreads), 0, stream,
+                                   x, rs.row_utt, rs.rows, dim, static_cast<const float2*>(mean_rstd), gamma, beta,
+                                   static_cast<__nv_bfloat16*>(out)));
     else if (prec == kPrecFp16)
-        groupnorm_apply_swish_kernel<__half><<<grid, kGnThreads, 0, stream>>>(
-            x, rs.row_utt, rs.rows, dim, mean_rstd, gamma, beta, static_cast<__half*>(out));
+        B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__half>, dim3(grid), dim3(kGnThreads), 0, stream, x,
+                                   rs.row_utt, rs.rows, dim, static_cast<const float2*>(mean_rstd), gamma, beta,
+                                   static_cast<__half*>(out)));
     else {
         set_error("groupnorm: unsupported precision %d", prec);
         return 1;
