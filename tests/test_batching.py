@@ -63,3 +63,17 @@ def test_decode_completions_matches_reward_loop():
         ref = ref[:, int(len(p) / dec.token_rate * dec.sample_rate):]
         assert wav.shape == ref.shape == (1, 320 * gen.numel())
         assert (wav - ref).abs().max().item() <= 1e-5 * max(1e-3, ref.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_decode_stream_windows_trims_to_new_audio():
+    g = torch.Generator().manual_seed(4)
+    dec = decoding.AudioDecoder(None, decoding.DecoderConfig("", 16000, 50, 320, None, None), device="cuda")
+    windows = [torch.randint(0, 65536, (n,), generator=g) for n in (150, 150, 80)]
+    out = batching.decode_stream_windows(dec, windows, [50, 50, 30])
+    for win, n_new, wav in zip(windows, (50, 50, 30), out):
+        ref = dec.decode(win)[:, -n_new * 320:]  # the reference forward on the same window, trimmed
+        assert wav.shape == ref.shape == (1, n_new * 320)
+        assert (wav - ref).abs().max().item() <= 1e-5 * max(1e-3, ref.abs().max().item())
+    with pytest.raises(ValueError):
+        batching.decode_stream_windows(dec, windows, [50, 50, 500])

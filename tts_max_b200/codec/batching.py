@@ -63,6 +63,27 @@ def decode_completions(
     return out  # type: ignore[return-value]
 
 
+def decode_stream_windows(
+    audio_decoder: AudioDecoder, windows: Sequence[torch.Tensor], new_tokens: Sequence[int] | int
+) -> list[torch.Tensor]:
+    """Chunked / streaming decode (BASELINE config 5): every element of `windows` is
+    `cat([left_context_ids, new_ids])`; all windows are decoded in one varlen batch and only the samples
+    of the trailing `new_tokens` tokens are returned. The reference has no streaming decode and chunking
+    changes GroupNorm / attention statistics, so the defined result is "the reference
+    forward on exactly this window, trimmed" -- which is what this returns."""
+    if isinstance(new_tokens, int):
+        new_tokens = [new_tokens] * len(windows)
+    if len(new_tokens) != len(windows):
+        raise ValueError("new_tokens must match windows")
+    hop = audio_decoder._decoder.hop_length
+    out = []
+    for wav, win, n_new in zip(audio_decoder.decode_batch(list(windows)), windows, new_tokens):
+        if not 0 < int(n_new) <= win.numel():
+            raise ValueError("new_tokens must be in (0, len(window)]")
+        out.append(wav[:, wav.shape[1] - int(n_new) * hop:])
+    return out
+
+
 class CodeStore:
     """Read-only view of the vectorizer's on-disk codes: flat int32 `codes` (memmap) + `index` offsets."""
 

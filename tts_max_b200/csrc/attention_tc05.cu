@@ -285,8 +285,8 @@ int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int hea
     const int D = heads * kD;
     if (make_tmap_2d(&tm, qkv, prec == kPrecBf16 ? 0 : 1, rs.rows, 3 * D, 3 * D, 128)) return 1;
     dim3 grid(rs.n_attn128_work, heads);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(attention_tc05_kernel<__nv_bfloat16>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal));
         B200_CUDA_OK(cudaFuncSetAttribute(attention_tc05_kernel<__half>,
@@ -298,7 +298,6 @@ int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int hea
         B200_CUDA_OK(cudaFuncSetAttribute(attention_tc05_kernel<__half>,
                                           cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
-        configured = true;
     }
     if (prec == kPrecBf16)
         B200_CUDA_OK(launch_kernel(attention_tc05_kernel<__nv_bfloat16>, grid, dim3(kThreads), AttnSmem::kTotal, stream,

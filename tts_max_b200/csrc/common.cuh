@@ -56,6 +56,20 @@ __device__ __forceinline__ void pdl_wait() {
 
 extern int g_use_pdl;  // codec.cu; 1 = on (default)
 
+// cudaFuncSetAttribute is per device: remember per (call site, device) whether it has been done, so a
+// process that holds decoders on several GPUs configures every kernel on each of them.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                  cudaStream_t stream, Args&&... args) {

@@ -296,11 +296,10 @@ int launch_gemm_tc05(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
                      cudaStream_t stream) {
     using SM = GemmSmem<BLOCK_N, kStages>;
     auto kern = gemm_tc05_kernel<BLOCK_N, InT, OutT, kStages>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SM::kTotal));
-        configured = true;
     }
     const int num_m = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int num_n = (p.n_store + BLOCK_N - 1) / BLOCK_N;

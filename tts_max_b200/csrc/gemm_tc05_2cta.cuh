@@ -396,11 +396,10 @@ template <typename InT, typename OutT>
 int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                           cudaStream_t stream) {
     auto kern = gemm_tc05_2cta_kernel<InT, OutT>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Gemm2Smem::kTotal));
-        configured = true;
     }
     const int num_m = (p.M + 255) / 256;
     const int num_n = p.n_store / kGemm2BlockN;

@@ -234,13 +234,12 @@ int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTab
                hop);
     B200_CHECK(ld >= 2 * kBins, "istft: ld %d < %d", ld, 2 * kBins);
     if (rs.n_istft_work <= 0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(IstftSmem))));
         B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
-        configured = true;
     }
     B200_CUDA_OK(launch_kernel(istft_kernel, dim3(rs.n_istft_work), dim3(kIstftThreads), sizeof(IstftSmem), stream,
                                x_pred, ld, rs.istft_work, rs.utt_row0, rs.utt_len, rs.utt_tok0, tab.twiddle,
