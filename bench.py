@@ -283,11 +283,14 @@ def run_ours(args):
     total_tokens = n_utts * tokens
     audio_s = n_utts * NEW_TOKENS.get(args.workload, tokens) / TOKEN_RATE
 
-    dec = decoder.Decoder(16000, HOP, None, None, precision=args.precision, init_seed=0)
+    if args.model == "48k":
+        dec = decoder.Decoder(48000, 160, [3, 2], [7, 6], precision=args.precision, init_seed=0)
+    else:
+        dec = decoder.Decoder(16000, HOP, None, None, precision=args.precision, init_seed=0)
     dec.to(dev).eval()
     ids_host = synthetic_ids(n_utts, tokens, 1234 + rank).pin_memory()
     ids_dev = ids_host.to(dev)
-    wav_host = torch.empty(total_tokens * HOP, dtype=torch.float32).pin_memory()
+    wav_host = torch.empty(total_tokens * dec.samples_per_token, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -407,7 +410,8 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "utterances_per_gpu": n_utts, "tokens_per_utterance": tokens,
+            "config": {"workload": f"{args.workload}: {desc}" + (" [48 kHz upsampler variant, not a BASELINE config]" if args.model == "48k" else ""),
+                       "utterances_per_gpu": n_utts, "tokens_per_utterance": tokens,
                        "audio_seconds_per_step_per_gpu": audio_s, "weights": "random-init, reference distributions (seed 0)",
                        "parallelism": f"dp{world} (independent utterances, no data-path collective)",
                        "l2": "256 MiB device buffer written between timed steps (outside the per-step event bracket)",
@@ -437,6 +441,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3"])
     ap.add_argument("--c3-utts", type=int, default=C3_UTTS)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--model", default="xcodec2", choices=["xcodec2", "48k"],
+                    help="xcodec2: 16 kHz, hop 320 (BASELINE configs); 48k: upsampler variant (hop 160, factors [3, 2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: plain stream-ordered launches instead of programmatic dependent launch")
     args = ap.parse_args()

@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B200CODEC_ABI_VERSION 1
+#define B200CODEC_ABI_VERSION 2
 
 /* arithmetic type of the tensor-core operands (accumulation is always fp32; the residual
  * stream, norms, softmax, FSQ lookup and ISTFT are always fp32). */
@@ -53,15 +53,16 @@ enum B200CodecDType { B200CODEC_F32 = 0, B200CODEC_F16 = 1, B200CODEC_BF16_T = 2
 typedef struct B200CodecConfig {
     int32_t abi_version;      /* must be B200CODEC_ABI_VERSION */
     int32_t sample_rate;      /* 16000 for xcodec2 */
-    int32_t hop_length;       /* 320; n_fft = win = 4 * hop (decoder_modules.py:426-431) */
-    int32_t n_upsample;       /* len(upsample_factors); must be 0 (upsampler is a NEXT row) */
+    int32_t hop_length;       /* 320 (xcodec2) or 160 (48 kHz); n_fft = win = 4 * hop (decoder_modules.py:426-431) */
+    int32_t n_upsample;       /* len(upsample_factors): 0 (xcodec2) .. 3 (UpSamplerBlock, upsampler.py:9-69) */
     int32_t precision;        /* enum B200CodecPrecision */
     int32_t device;           /* CUDA device ordinal */
     int32_t hidden_dim;       /* 1024 */
     int32_t depth;            /* 12 transformer blocks */
     int32_t heads;            /* 16 */
     int32_t vq_dim;           /* 2048 */
-    int32_t reserved[6];
+    int32_t upsample_factors[3]; /* e.g. {3, 2, 0}: ConvTranspose1d strides (decoder.py:48-53) */
+    int32_t kernel_sizes[3];     /* e.g. {7, 6, 0}: ConvTranspose1d kernel sizes, padding (k - u) / 2 */
 } B200CodecConfig;
 
 typedef struct B200Codec B200Codec;
@@ -102,7 +103,8 @@ int b200codec_finalize_weights(B200Codec* h, void* stream);
 
 /* Replaces Decoder.forward (tts/core/codec/decoder.py:69-89) for a VARLEN batch: utterance
  * u has seqlens_host[u] tokens, ids are packed back to back, waveforms are packed back to
- * back with hop_length * seqlens[u] samples each. Every utterance is decoded with exactly
+ * back with hop_length * prod(upsample_factors) * seqlens[u] samples each
+ * (b200codec_samples_per_token: 320 for xcodec2, 960 for the 48 kHz config). Every utterance is decoded with exactly
  * the single-utterance semantics of the reference (per-utterance GroupNorm statistics,
  * unmasked attention within the utterance, zero conv padding at the utterance edges), so an
  * equal-length batch reproduces the reference's batched forward row for row.
@@ -132,6 +134,9 @@ int b200codec_set_attention_impl(int impl);
 /* Process-wide: launch the kernel chain with programmatic dependent launch (1, default) or as
  * plain stream-ordered launches (0; for A/B measurements). */
 int b200codec_set_pdl(int on);
+
+/* output samples per input token: hop_length * prod(upsample_factors) */
+int b200codec_samples_per_token(const B200Codec* h);
 
 /* number of kernels the library launched since creation (bench.py's gpu_launches) */
 int64_t b200codec_launch_count(const B200Codec* h);

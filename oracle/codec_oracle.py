@@ -172,24 +172,50 @@ def istft_head(sd: SD, x: torch.Tensor, hop: int) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
-# decoder.py:69-89  Decoder.forward (upsampler is None for the xcodec2 config)
+# upsampler.py:9-69  UpSamplerBlock (48 kHz variant): weight-normed ConvTranspose1d + ResnetBlock per
+# factor, then out_proj + swish. ResnetBlock is built with the default temb_channels=512, so its
+# state dict carries an unused temb_proj (forward is called with temb=None, decoder_modules.py:209).
+# ---------------------------------------------------------------------------------------------
+def weight_norm_weight(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """torch.nn.utils.weight_norm (dim=0): w = g * v / ||v||, the norm taken over all dims but 0."""
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+    return v * (g / norm)
+
+
+def upsampler(sd: SD, x: torch.Tensor, factors, kernels) -> torch.Tensor:
+    """x (B, C, T) -> (B, T * prod(factors), C). upsampler.py:62-69."""
+    for i, (k, u) in enumerate(zip(kernels, factors)):
+        p = f"upsampler.upsample_layers.{i}."
+        w = weight_norm_weight(sd[p + "weight_g"], sd[p + "weight_v"])
+        x = F.conv_transpose1d(x, w, sd[p + "bias"], stride=u, padding=(k - u) // 2)
+        x = resnet_block(sd, f"upsampler.resnet_blocks.{i}.", x)
+    x = F.linear(x.transpose(1, 2), sd["upsampler.out_proj.weight"], sd["upsampler.out_proj.bias"])
+    return swish(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder.py:69-89  Decoder.forward
 # ---------------------------------------------------------------------------------------------
 @torch.no_grad()
-def decoder_forward(sd: SD, vq_codes: torch.Tensor, hop: int = 320, depth: int = DEPTH, stages: dict | None = None) -> torch.Tensor:
-    """vq_codes (B, T) or (B, 1, T) -> (B, 1, hop * T) float32. `stages`, if given, receives the
-    intermediate tensors (K1 output, fc_post_a output, backbone output, head Linear output)."""
+def decoder_forward(sd: SD, vq_codes: torch.Tensor, hop: int = 320, depth: int = DEPTH, stages: dict | None = None,
+                    upsample_factors=None, kernel_sizes=None) -> torch.Tensor:
+    """vq_codes (B, T) or (B, 1, T) -> (B, 1, hop * prod(upsample_factors) * T) float32. `stages`, if
+    given, receives the intermediate tensors (K1 output, fc_post_a output, backbone output, upsampler
+    output, head Linear output)."""
     if vq_codes.dim() == 2:
         vq_codes = vq_codes.unsqueeze(1)
     ids = vq_codes.transpose(1, 2)[..., 0]  # (B, T)
     emb = fsq_lookup(sd, ids)
     x = F.linear(emb, sd["fc_post_a.weight"], sd["fc_post_a.bias"])
     hidden = backbone(sd, x, depth)
+    up = upsampler(sd, hidden.transpose(1, 2), upsample_factors, kernel_sizes) if upsample_factors else hidden
     if stages is not None:
         stages["fsq"] = emb
         stages["fc_post_a"] = x
         stages["backbone"] = hidden
-        stages["head_linear"] = F.linear(hidden, sd["decoder.head.out.weight"], sd["decoder.head.out.bias"])
-    return istft_head(sd, hidden, hop)
+        stages["upsampled"] = up
+        stages["head_linear"] = F.linear(up, sd["decoder.head.out.weight"], sd["decoder.head.out.bias"])
+    return istft_head(sd, up, hop)
 
 
 def snr_db(ref: torch.Tensor, test: torch.Tensor) -> float:

@@ -20,7 +20,7 @@ import torch
 C, V, DEPTH = 1024, 2048, 12
 
 
-def shapes(hop: int = 320, depth: int = DEPTH):
+def shapes(hop: int = 320, depth: int = DEPTH, upsample_factors=None, kernel_sizes=None):
     n_fft = 4 * hop
     sd = collections.OrderedDict()
     g = "decoder."
@@ -55,6 +55,30 @@ def shapes(hop: int = 320, depth: int = DEPTH):
     sd[g + "head.out.weight"] = (n_fft + 2, C)
     sd[g + "head.out.bias"] = (n_fft + 2,)
     sd[g + "head.istft.window"] = (n_fft,)
+    if upsample_factors:
+        # registration order of UpSamplerBlock.__init__ (upsampler.py:27-60): upsample_layers,
+        # resnet_blocks, out_proj; Decoder registers `upsampler` before `fc_post_a` (decoder.py:48-63)
+        n = len(upsample_factors)
+        for i, k in enumerate(kernel_sizes):
+            cin, cout = C // (2 ** i), C // (2 ** (i + 1))
+            sd[f"upsampler.upsample_layers.{i}.bias"] = (cout,)
+            sd[f"upsampler.upsample_layers.{i}.weight_g"] = (cin, 1, 1)
+            sd[f"upsampler.upsample_layers.{i}.weight_v"] = (cin, cout, k)
+        for i in range(n):
+            c = C // (2 ** (i + 1))
+            p = f"upsampler.resnet_blocks.{i}."
+            sd[p + "norm1.weight"] = (c,)
+            sd[p + "norm1.bias"] = (c,)
+            sd[p + "conv1.weight"] = (c, c, 3)
+            sd[p + "conv1.bias"] = (c,)
+            sd[p + "temb_proj.weight"] = (c, 512)
+            sd[p + "temb_proj.bias"] = (c,)
+            sd[p + "norm2.weight"] = (c,)
+            sd[p + "norm2.bias"] = (c,)
+            sd[p + "conv2.weight"] = (c, c, 3)
+            sd[p + "conv2.bias"] = (c,)
+        sd["upsampler.out_proj.weight"] = (C, C // (2 ** n))
+        sd["upsampler.out_proj.bias"] = (C,)
     sd["fc_post_a.weight"] = (C, V)
     sd["fc_post_a.bias"] = (C,)
     return sd
@@ -64,13 +88,20 @@ def _gen(seed: int, key: str) -> torch.Generator:
     return torch.Generator().manual_seed((seed * 1_000_003 + zlib.crc32(key.encode())) % (2 ** 31))
 
 
-def make_state_dict(seed: int = 0, perturb: bool = True, hop: int = 320, depth: int = DEPTH):
-    all_shapes = shapes(hop, depth)
+def make_state_dict(seed: int = 0, perturb: bool = True, hop: int = 320, depth: int = DEPTH,
+                    upsample_factors=None, kernel_sizes=None):
+    all_shapes = shapes(hop, depth, upsample_factors, kernel_sizes)
     out = collections.OrderedDict()
     for key, shape in all_shapes.items():
         g = _gen(seed, key)
         if key.endswith("istft.window"):
             t = torch.hann_window(shape[0])
+        elif key.endswith("weight_g"):
+            # weight_norm initialises g to ||v||; perturbed so that g actually matters
+            t = 0.35 + 0.1 * torch.rand(shape, generator=g)
+        elif key.endswith("weight_v"):
+            fan = shape[1] * shape[2]
+            t = (torch.rand(shape, generator=g) * 2.0 - 1.0) / math.sqrt(fan)
         elif "norm" in key:
             if key.endswith("weight"):
                 t = 1.0 + 0.2 * torch.randn(shape, generator=g) if perturb else torch.ones(shape)
@@ -79,7 +110,7 @@ def make_state_dict(seed: int = 0, perturb: bool = True, hop: int = 320, depth: 
         elif len(shape) == 3:
             t = torch.empty(shape)
             torch.nn.init.trunc_normal_(t, std=0.02, generator=g)
-        elif key.endswith("bias") and ("embed" in key or "conv" in key):
+        elif key.endswith("bias") and ("embed" in key or "conv" in key or "upsample_layers" in key):
             t = 0.05 * torch.randn(shape, generator=g) if perturb else torch.zeros(shape)
         else:
             wshape = shape if len(shape) == 2 else all_shapes[key[: -len("bias")] + "weight"]

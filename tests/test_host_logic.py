@@ -37,8 +37,12 @@ def test_create_requires_model_config(tmp_path):
 def test_rate_check_matches_reference():
     with pytest.raises(ValueError, match="do not match the target"):
         decoder.Decoder(16000, 300, None, None)
+    with pytest.raises(ValueError, match="do not match the target"):
+        decoder.Decoder(48000, 160, [3, 2, 2], [7, 6, 4])
     with pytest.raises(NotImplementedError):
-        decoder.Decoder(48000, 160, [3, 2], [7, 6])  # upsampler variant: NEXT row
+        decoder.Decoder(96000, 160, [3, 2, 2], [7, 6, 4])  # three stages are not instantiated
+    d = decoder.Decoder(48000, 160, [3, 2], [7, 6], init_seed=0)  # the 48 kHz upsampler variant
+    assert d.samples_per_token == 960 and len(d.state_dict()) == 145
 
 
 def test_state_dict_contract(golden, state_dict):

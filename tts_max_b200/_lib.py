@@ -10,7 +10,7 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PRECISIONS = {"bf16": 0, "fp16": 1}
 IDS_I32, IDS_I64 = 0, 1
 DT_F32, DT_F16, DT_BF16, DT_F64 = 0, 1, 2, 3
@@ -30,7 +30,8 @@ class B200CodecConfig(ctypes.Structure):
         ("depth", c_int32),
         ("heads", c_int32),
         ("vq_dim", c_int32),
-        ("reserved", c_int32 * 6),
+        ("upsample_factors", c_int32 * 3),
+        ("kernel_sizes", c_int32 * 3),
     ]
 
 
@@ -50,6 +51,7 @@ SIGNATURES = {
     "b200codec_take_id_error": (c_int, [c_void_p]),
     "b200codec_set_attention_impl": (c_int, [c_int]),
     "b200codec_set_pdl": (c_int, [c_int]),
+    "b200codec_samples_per_token": (c_int, [c_void_p]),
     "b200codec_launch_count": (c_int64, [c_void_p]),
     "b200codec_profile": (c_int, [c_void_p, c_int]),
     "b200codec_stage_times": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),

@@ -75,7 +75,7 @@ def decode_stream_windows(
         new_tokens = [new_tokens] * len(windows)
     if len(new_tokens) != len(windows):
         raise ValueError("new_tokens must match windows")
-    hop = audio_decoder._decoder.hop_length
+    hop = audio_decoder._decoder.samples_per_token
     out = []
     for wav, win, n_new in zip(audio_decoder.decode_batch(list(windows)), windows, new_tokens):
         if not 0 < int(n_new) <= win.numel():
@@ -126,7 +126,7 @@ def decode_code_store(
         if lengths[i] <= 0:
             raise ValueError(f"sample {i} has no codes")
     dec = audio_decoder._decoder
-    hop = dec.hop_length
+    hop = dec.samples_per_token
     for bucket in sharding.bucket_by_length(ids, lengths, max_tokens=max_tokens):
         seqlens = [lengths[i] for i in bucket]
         packed = np.concatenate([store.codes[slice(*store.span(i))] for i in bucket]).astype(np.int32, copy=False)

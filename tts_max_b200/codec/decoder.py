@@ -28,10 +28,14 @@ HEADS = 16
 VQ_DIM = 2048
 
 
-def expected_state_dict_shapes(hop_length: int = 320, depth: int = DEPTH) -> "collections.OrderedDict[str, tuple[int, ...]]":
-    """Keys and shapes of `Decoder.state_dict()` for the xcodec2 config, in module order
-    (reference: `Generator.__init__` decoder_modules.py:403-433, `VocosBackbone.__init__`
-    :330-388, `Decoder.__init__` decoder.py:46-63)."""
+def expected_state_dict_shapes(
+    hop_length: int = 320, depth: int = DEPTH, upsample_factors: Sequence[int] | None = None,
+    kernel_sizes: Sequence[int] | None = None,
+) -> "collections.OrderedDict[str, tuple[int, ...]]":
+    """Keys and shapes of `Decoder.state_dict()`, in module order (reference: `Generator.__init__`
+    decoder_modules.py:403-433, `VocosBackbone.__init__` :330-388, `UpSamplerBlock.__init__`
+    upsampler.py:12-60, `Decoder.__init__` decoder.py:46-63). 117 tensors for the xcodec2 config, 145 for
+    the 48 kHz config with upsample_factors [3, 2]."""
     C, V, n_fft = HIDDEN_DIM, VQ_DIM, 4 * hop_length
     sd: "collections.OrderedDict[str, tuple[int, ...]]" = collections.OrderedDict()
     g = "decoder."
@@ -66,21 +70,55 @@ def expected_state_dict_shapes(hop_length: int = 320, depth: int = DEPTH) -> "co
     sd[g + "head.out.weight"] = (n_fft + 2, C)
     sd[g + "head.out.bias"] = (n_fft + 2,)
     sd[g + "head.istft.window"] = (n_fft,)
+    if upsample_factors:
+        n = len(upsample_factors)
+        for i, k in enumerate(kernel_sizes):
+            cin, cout = C // (2 ** i), C // (2 ** (i + 1))
+            sd[f"upsampler.upsample_layers.{i}.bias"] = (cout,)
+            sd[f"upsampler.upsample_layers.{i}.weight_g"] = (cin, 1, 1)
+            sd[f"upsampler.upsample_layers.{i}.weight_v"] = (cin, cout, k)
+        for i in range(n):
+            c = C // (2 ** (i + 1))
+            p = f"upsampler.resnet_blocks.{i}."
+            sd[p + "norm1.weight"] = (c,)
+            sd[p + "norm1.bias"] = (c,)
+            sd[p + "conv1.weight"] = (c, c, 3)
+            sd[p + "conv1.bias"] = (c,)
+            sd[p + "temb_proj.weight"] = (c, 512)  # built with the default temb_channels; unused (temb=None)
+            sd[p + "temb_proj.bias"] = (c,)
+            sd[p + "norm2.weight"] = (c,)
+            sd[p + "norm2.bias"] = (c,)
+            sd[p + "conv2.weight"] = (c, c, 3)
+            sd[p + "conv2.bias"] = (c,)
+        sd["upsampler.out_proj.weight"] = (C, C // (2 ** n))
+        sd["upsampler.out_proj.bias"] = (C,)
     sd["fc_post_a.weight"] = (C, V)
     sd["fc_post_a.bias"] = (C,)
     return sd
 
 
-def random_init_state_dict(hop_length: int = 320, seed: int | None = None) -> "collections.OrderedDict[str, torch.Tensor]":
+def random_init_state_dict(
+    hop_length: int = 320, seed: int | None = None, upsample_factors: Sequence[int] | None = None,
+    kernel_sizes: Sequence[int] | None = None,
+) -> "collections.OrderedDict[str, torch.Tensor]":
     """Random initialisation with the reference's distributions (not its RNG stream):
     Conv1d weight trunc_normal(std=0.02) / bias 0 (decoder_modules.py:13-16, 463-464),
     Linear = torch default (kaiming_uniform(a=sqrt(5)) -> U(+-1/sqrt(fan_in)) for weight and
     bias), norm weight 1 / bias 0, `window` = periodic hann (decoder_modules.py:32-33)."""
     gen = torch.Generator().manual_seed(seed) if seed is not None else None
     out: "collections.OrderedDict[str, torch.Tensor]" = collections.OrderedDict()
-    for key, shape in expected_state_dict_shapes(hop_length).items():
+    all_shapes = expected_state_dict_shapes(hop_length, DEPTH, upsample_factors, kernel_sizes)
+    pending_g: dict[str, torch.Tensor] = {}
+    for key, shape in all_shapes.items():
         if key.endswith("istft.window"):
             t = torch.hann_window(shape[0])
+        elif key.endswith("weight_g"):
+            t = torch.ones(shape)  # replaced by ||v|| below (torch.nn.utils.weight_norm initialisation)
+        elif key.endswith("weight_v"):
+            # ConvTranspose1d default init: kaiming_uniform(a=sqrt(5)) with fan_in = Cout * k
+            bound = 1.0 / math.sqrt(shape[1] * shape[2])
+            t = (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
+            pending_g[key[: -len("weight_v")] + "weight_g"] = t.reshape(shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
         elif "norm" in key:
             t = torch.ones(shape) if key.endswith("weight") else torch.zeros(shape)
         elif len(shape) == 3:  # Conv1d weight
@@ -88,11 +126,17 @@ def random_init_state_dict(hop_length: int = 320, seed: int | None = None) -> "c
             torch.nn.init.trunc_normal_(t, std=0.02, generator=gen)
         elif key.endswith("bias") and ("embed" in key or "conv" in key):
             t = torch.zeros(shape)
+        elif key.endswith("bias") and "upsample_layers" in key:
+            wv = all_shapes[key[: -len("bias")] + "weight_v"]
+            bound = 1.0 / math.sqrt(wv[1] * wv[2])
+            t = (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
         else:  # Linear weight / bias: bound = 1 / sqrt(fan_in)
-            wshape = shape if len(shape) == 2 else expected_state_dict_shapes(hop_length)[key[: -len("bias")] + "weight"]
+            wshape = shape if len(shape) == 2 else all_shapes[key[: -len("bias")] + "weight"]
             bound = 1.0 / math.sqrt(wshape[1])
             t = (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
         out[key] = t.to(torch.float32).contiguous()
+    for key, g in pending_g.items():
+        out[key] = g.to(torch.float32).contiguous()
     return out
 
 
@@ -134,16 +178,20 @@ class Decoder(torch.nn.Module):
                 f"sample rate {self.sample_rate}."
             )
         if self.upsample_factors:
-            raise NotImplementedError(
-                "upsample_factors are not supported yet: the 48 kHz UpSamplerBlock variant "
-                "(tts/core/codec/upsampler.py) is a NEXT row (SURVEY.md 8f-1)"
-            )
-        if self.hop_length != 320:
-            raise NotImplementedError("only hop_length == 320 (xcodec2, 16 kHz) is instantiated")
+            if not self.kernel_sizes or len(self.kernel_sizes) != len(self.upsample_factors):
+                raise ValueError("kernel_sizes must match upsample_factors")
+            if len(self.upsample_factors) > 2 or any((k - u) % 2 or k < u for k, u in zip(self.kernel_sizes, self.upsample_factors)):
+                raise NotImplementedError(
+                    f"upsampler configuration factors={self.upsample_factors} kernels={self.kernel_sizes} is not "
+                    "instantiated (at most two stages, kernel - factor even)")
+        if self.hop_length not in (320, 160):
+            raise NotImplementedError("only hop_length 320 (n_fft 1280) and 160 (n_fft 640) are instantiated")
+        self.samples_per_token = self.hop_length * total_ups
 
-        self._shapes = expected_state_dict_shapes(hop_length)
+        self._shapes = expected_state_dict_shapes(hop_length, DEPTH, self.upsample_factors, self.kernel_sizes)
         # host fp32 copy of the weights; the library holds the device copies once .to(cuda) ran
-        self._host_state: "collections.OrderedDict[str, torch.Tensor]" = random_init_state_dict(hop_length, init_seed)
+        self._host_state: "collections.OrderedDict[str, torch.Tensor]" = random_init_state_dict(
+            hop_length, init_seed, self.upsample_factors, self.kernel_sizes)
         self._handle: ctypes.c_void_p | None = None
         self._device: torch.device = torch.device("cpu")
         self._dirty = True
@@ -254,10 +302,14 @@ class Decoder(torch.nn.Module):
             )
         lib = _lib.load()
         if self._handle is None:
+            ups = list(self.upsample_factors or [])
+            ks = list(self.kernel_sizes or []) if ups else []
             cfg = _lib.B200CodecConfig(
                 abi_version=_lib.ABI_VERSION, sample_rate=self.sample_rate, hop_length=self.hop_length,
-                n_upsample=len(self.upsample_factors or []), precision=_lib.PRECISIONS[self.precision],
+                n_upsample=len(ups), precision=_lib.PRECISIONS[self.precision],
                 device=self._device.index or 0, hidden_dim=HIDDEN_DIM, depth=DEPTH, heads=HEADS, vq_dim=VQ_DIM,
+                upsample_factors=(ctypes.c_int32 * 3)(*(ups + [0] * (3 - len(ups)))),
+                kernel_sizes=(ctypes.c_int32 * 3)(*(ks + [0] * (3 - len(ks)))),
             )
             handle = ctypes.c_void_p()
             _lib.check(lib.b200codec_create(ctypes.byref(cfg), ctypes.byref(handle)))
@@ -278,7 +330,7 @@ class Decoder(torch.nn.Module):
     @torch.no_grad()
     def forward(self, vq_codes: torch.Tensor) -> torch.Tensor:
         """vq_codes: (batch, codes_length) or (batch, 1, codes_length) integer ids ->
-        (batch, 1, hop_length * codes_length) float32 on the decoder's device
+        (batch, 1, hop_length * prod(upsample_factors) * codes_length) float32 on the decoder's device
         (reference: decoder.py:69-89)."""
         if vq_codes.dim() == 2:
             vq_codes = vq_codes.unsqueeze(1)
@@ -294,7 +346,7 @@ class Decoder(torch.nn.Module):
         handle = self._ensure_handle()
         ids = vq_codes.to(self._device).reshape(batch * length).contiguous()
         wavs = self.decode_packed_device(ids, [length] * batch)
-        return wavs.view(batch, 1, self.hop_length * length)
+        return wavs.view(batch, 1, self.samples_per_token * length)
 
     @torch.no_grad()
     def decode_packed_device(self, ids: torch.Tensor, seqlens: Sequence[int]) -> torch.Tensor:
@@ -307,7 +359,7 @@ class Decoder(torch.nn.Module):
             raise ValueError("ids must be a packed 1-D tensor on the decoder's device matching seqlens")
         id_type = _lib.IDS_I64 if ids.dtype == torch.int64 else _lib.IDS_I32
         with torch.cuda.device(self._device):
-            wav = torch.empty(total * self.hop_length, dtype=torch.float32, device=self._device)
+            wav = torch.empty(total * self.samples_per_token, dtype=torch.float32, device=self._device)
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(lib.b200codec_decode_varlen(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
                                                    _lib.i32_array(seqlens), len(seqlens),
@@ -328,7 +380,7 @@ class Decoder(torch.nn.Module):
         ids = ids.contiguous()
         id_type = _lib.IDS_I64 if ids.dtype == torch.int64 else _lib.IDS_I32
         if out is None:
-            out = torch.empty(total * self.hop_length, dtype=torch.float32, pin_memory=True)
+            out = torch.empty(total * self.samples_per_token, dtype=torch.float32, pin_memory=True)
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(lib.b200codec_decode_host(handle, ctypes.c_void_p(ids.data_ptr()), id_type,

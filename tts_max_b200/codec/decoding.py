@@ -126,7 +126,7 @@ class AudioDecoder(AudioDecoderInterface):
                 raise ValueError("decode_batch: every element must be a non-empty 1-D id tensor")
         packed = torch.cat([t.detach().to("cpu", torch.int64) for t in speech_ids])
         wav = self._decoder.decode_packed_host(packed, seqlens)
-        hop = self._decoder.hop_length
+        hop = self._decoder.samples_per_token
         out, off = [], 0
         for n in seqlens:
             out.append(wav[off * hop:(off + n) * hop].view(1, -1))

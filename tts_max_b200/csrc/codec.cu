@@ -46,7 +46,7 @@ int run_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void
 }
 
 constexpr int kGap = 3;          // zero rows between utterances (conv7 halo)
-constexpr int kHeadLd = 1344;    // head.out columns padded to a multiple of 32 (1282 -> 1344)
+constexpr int kMaxUp = 3;        // upsampler stages (UpSamplerBlock, tts/core/codec/upsampler.py)
 
 struct TensorSpec {
     std::string key;
@@ -92,6 +92,19 @@ struct LayerW {
     void *qkv, *proj, *fc1, *fc2;
 };
 
+// one ConvTranspose1d output phase as an ordinary row-shifted conv (see finalize)
+struct UpPhase {
+    void* w = nullptr;  // operand dtype [Cout, taps * Cin]
+    int taps = 0;
+    int pad = 0;        // A row = m + tap - pad
+};
+struct UpStageW {
+    int Cin = 0, Cout = 0, stride = 0, k = 0;
+    UpPhase phase[8];
+    const float* bias = nullptr;
+    ResBlockW res;
+};
+
 struct StageTimer {
     std::string name;
     cudaEvent_t a, b;
@@ -105,6 +118,8 @@ using namespace b200;
 struct B200Codec {
     B200CodecConfig cfg;
     int C, H, L, V, hop, n_fft, n_bins;
+    int n_up = 0, total_up = 1, head_ld = 0;  // upsampler stages, prod(factors), padded head.out width
+    int up_f[kMaxUp] = {0, 0, 0}, up_k[kMaxUp] = {0, 0, 0};
     std::vector<TensorSpec> specs;
     std::map<std::string, int> index;
     std::vector<float*> master;  // fp32 device copies, nullptr until loaded
@@ -117,6 +132,8 @@ struct B200Codec {
     ResBlockW res[4];
     LayerW layers[64];
     void* w_head = nullptr;
+    UpStageW up[kMaxUp];
+    void* w_out_proj = nullptr;
     float* head_bias_pad = nullptr;
     float2* twiddle = nullptr;
     float *rope_cos = nullptr, *rope_sin = nullptr;
@@ -126,15 +143,21 @@ struct B200Codec {
     int ws_rows = 0;
     void *a0, *xc, *an, *qkv, *y, *f, *xb;  // operand dtype
     float *x, *hbuf, *ho, *ss;
+    // upsampler stage i lives in row space plan[i + 1] at up[i].Cout channels
+    float *u_x[kMaxUp], *u_h[kMaxUp];
+    void *u_an[kMaxUp], *u_a16[kMaxUp];
+    void* u_fin = nullptr;  // out_proj + swish output, operand dtype [rows_last, C]
     double* gn_stats = nullptr;
     size_t gn_stats_bytes = 0;
-    // plan (row space) cache
-    DevBuf plan_dev;
+    int gn_slots = 8;  // GroupNorm layers: 8 in the backbone + 2 per upsampler stage
+    // plan (row space) cache; plan i > 0 is the row space after upsampler stage i - 1
+    // (every length, offset and gap of plan 0 multiplied by the product of the strides so far)
+    DevBuf plan_dev, plan_up_dev[kMaxUp];
     void* plan_host = nullptr;
     size_t plan_host_bytes = 0;
     std::vector<int32_t> plan_key;
     int plan_gap = -1;
-    RowSpace rs;
+    RowSpace rs, rs_up[kMaxUp];
     // io staging for decode_host
     DevBuf io_ids, io_wav;
     int* err_flag_host = nullptr;  // mapped pinned
@@ -199,6 +222,32 @@ void build_specs(B200Codec* h) {
     add_spec(h, g + "head.out.weight", {h->n_fft + 2, C});
     add_spec(h, g + "head.out.bias", {h->n_fft + 2});
     add_spec(h, g + "head.istft.window", {h->n_fft});
+    // UpSamplerBlock (upsampler.py:27-60), registered before fc_post_a (decoder.py:48-63)
+    for (int i = 0; i < h->n_up; ++i) {
+        const std::string p = "upsampler.upsample_layers." + std::to_string(i) + ".";
+        const int64_t cin = C >> i, cout = C >> (i + 1);
+        add_spec(h, p + "bias", {cout});
+        add_spec(h, p + "weight_g", {cin, 1, 1});
+        add_spec(h, p + "weight_v", {cin, cout, h->up_k[i]});
+    }
+    for (int i = 0; i < h->n_up; ++i) {
+        const std::string p = "upsampler.resnet_blocks." + std::to_string(i) + ".";
+        const int64_t c = C >> (i + 1);
+        add_spec(h, p + "norm1.weight", {c});
+        add_spec(h, p + "norm1.bias", {c});
+        add_spec(h, p + "conv1.weight", {c, c, 3});
+        add_spec(h, p + "conv1.bias", {c});
+        add_spec(h, p + "temb_proj.weight", {c, 512});  // unused at inference (temb=None), but in the state dict
+        add_spec(h, p + "temb_proj.bias", {c});
+        add_spec(h, p + "norm2.weight", {c});
+        add_spec(h, p + "norm2.bias", {c});
+        add_spec(h, p + "conv2.weight", {c, c, 3});
+        add_spec(h, p + "conv2.bias", {c});
+    }
+    if (h->n_up > 0) {
+        add_spec(h, "upsampler.out_proj.weight", {C, C >> h->n_up});
+        add_spec(h, "upsampler.out_proj.bias", {C});
+    }
     add_spec(h, "fc_post_a.weight", {C, V});
     add_spec(h, "fc_post_a.bias", {C});
 }
@@ -330,6 +379,28 @@ int build_plan(B200Codec* h, const int32_t* seqlens, int n_utts, int gap, cudaSt
                                  stream));
     B200_CUDA_OK(cudaStreamSynchronize(stream));  // plan_host is reused by the next build
     plan_bind(L, h->plan_dev.p, &h->rs);
+    // upsampled row spaces: out row = stride * in row + phase, so everything scales by the stride
+    int factor = 1;
+    std::vector<int32_t> scaled(n_utts);
+    for (int i = 0; i < h->n_up; ++i) {
+        factor *= h->up_f[i];
+        for (int u = 0; u < n_utts; ++u) scaled[u] = seqlens[u] * factor;
+        PlanLayout Lu;
+        if (plan_layout(scaled.data(), n_utts, gap * factor, &Lu)) return 1;
+        if (Lu.total_bytes > h->plan_host_bytes) {
+            cudaFreeHost(h->plan_host);
+            h->plan_host = nullptr;
+            h->plan_host_bytes = 0;
+            B200_CUDA_OK(cudaMallocHost(&h->plan_host, Lu.total_bytes * 2));
+            h->plan_host_bytes = Lu.total_bytes * 2;
+        }
+        if (h->plan_up_dev[i].ensure(Lu.total_bytes)) return 1;
+        plan_fill(Lu, scaled.data(), gap * factor, h->plan_host);
+        B200_CUDA_OK(cudaMemcpyAsync(h->plan_up_dev[i].p, h->plan_host, Lu.total_bytes, cudaMemcpyHostToDevice,
+                                     stream));
+        B200_CUDA_OK(cudaStreamSynchronize(stream));
+        plan_bind(Lu, h->plan_up_dev[i].p, &h->rs_up[i]);
+    }
     h->plan_key.assign(seqlens, seqlens + n_utts);
     h->plan_gap = gap;
     return 0;
@@ -361,10 +432,23 @@ int ensure_workspace(B200Codec* h, int rows) {
     const size_t es = operand_bytes(h->cfg.precision);
     const size_t C = h->C;
     auto al = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
+    const size_t Rlast = R * h->total_up;  // rows of the last (upsampled) row space
     size_t sz_a0 = al(R * h->V * es), sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
-           sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(R * kHeadLd * 4);
+           sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(Rlast * h->head_ld * 4);
     size_t sz_ss = al(R * 8 * 4);
     size_t total = sz_a0 + 4 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho + sz_ss;
+    size_t up_rows[kMaxUp], sz_up32[kMaxUp], sz_up16[kMaxUp];
+    {
+        size_t f = 1;
+        for (int i = 0; i < h->n_up; ++i) {
+            f *= h->up_f[i];
+            up_rows[i] = R * f;
+            sz_up32[i] = al(up_rows[i] * h->up[i].Cout * 4);
+            sz_up16[i] = al(up_rows[i] * h->up[i].Cout * es);
+            total += 2 * sz_up32[i] + 2 * sz_up16[i];
+        }
+        if (h->n_up > 0) total += al(Rlast * C * es);
+    }
     h->ws.release();
     h->ws_rows = 0;
     if (h->ws.ensure(total)) return 1;
@@ -381,6 +465,13 @@ int ensure_workspace(B200Codec* h, int rows) {
     h->hbuf = reinterpret_cast<float*>(p); p += sz_x;
     h->ho = reinterpret_cast<float*>(p); p += sz_ho;
     h->ss = reinterpret_cast<float*>(p); p += sz_ss;
+    for (int i = 0; i < h->n_up; ++i) {
+        h->u_x[i] = reinterpret_cast<float*>(p); p += sz_up32[i];
+        h->u_h[i] = reinterpret_cast<float*>(p); p += sz_up32[i];
+        h->u_an[i] = p; p += sz_up16[i];
+        h->u_a16[i] = p; p += sz_up16[i];
+    }
+    if (h->n_up > 0) { h->u_fin = p; p += al(Rlast * C * es); }
     h->ws_rows = static_cast<int>(R);
     return 0;
 }
@@ -464,34 +555,143 @@ int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, v
     return launch_gemm(c, s);
 }
 
-int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t s,
-                 const NormFuse& nf = NormFuse()) {
-    const int C = h->C, prec = h->cfg.precision;
-    const RowSpace& rs = h->rs;
+// ResnetBlock (decoder_modules.py:201-223) on one row space at C channels:
+//   x <- x + conv2(swish(GN2(conv1(swish(GN1(x))))))
+struct ResCtx {
+    const RowSpace* rs;
+    int C;
+    float* x;        // fp32 [rows, C], updated in place
+    float* hb;       // fp32 scratch [rows, C]
+    void* an;        // operand scratch [rows, C]
+    bool mask_out;   // write zeros on halo rows of x / out16 (x feeds a (transposed) conv directly)
+};
+
+int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stats_slot, cudaStream_t s,
+                    const NormFuse& nf) {
+    const int C = cx.C, prec = h->cfg.precision;
+    const RowSpace& rs = *cx.rs;
     double* st1 = h->gn_stats + static_cast<size_t>(stats_slot) * rs.n_utts * 64;
     double* st2 = st1 + static_cast<size_t>(rs.n_utts) * 64;
-    float2* mr_base = reinterpret_cast<float2*>(h->gn_stats + static_cast<size_t>(8) * rs.n_utts * 64);
+    float2* mr_base = reinterpret_cast<float2*>(h->gn_stats + static_cast<size_t>(h->gn_slots) * rs.n_utts * 64);
     float2* mr1 = mr_base + static_cast<size_t>(stats_slot) * rs.n_utts * 32;
     float2* mr2 = mr1 + static_cast<size_t>(rs.n_utts) * 32;
+    auto conv3 = [&](const void* a, const void* wt, float* out, const float* bias, const float* residual,
+                     bool mask, const NormFuse& f) {
+        GemmCall c;
+        c.precision = prec;
+        c.a = a;
+        c.a_rows = rs.rows;
+        c.Cin = C;
+        c.w = wt;
+        c.N = C;
+        c.taps = 3;
+        c.out = out;
+        c.out_fp32 = 1;
+        c.ldc = C;
+        c.n_store = C;
+        c.bias = bias;
+        c.residual = residual;
+        c.ld_res = C;
+        c.row_valid = mask ? rs.row_valid : nullptr;
+        c.act = kActNone;
+        c.ss_in = f.ss_in;
+        c.ss_inv_dim = 1.f / static_cast<float>(C);
+        c.ss_eps = 1e-6f;
+        c.out16 = f.out16;
+        c.ld16 = C;
+        c.ss_out = f.ss_out;
+        return launch_gemm(c, s);
+    };
     {
         Stage t(h, "groupnorm_swish", s);
-        RUN(launch_groupnorm_stats(h->x, rs, C, st1, s));
-        RUN(launch_groupnorm_apply_swish(prec, h->x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, h->an, s, mr1));
+        RUN(launch_groupnorm_stats(cx.x, rs, C, st1, s));
+        RUN(launch_groupnorm_apply_swish(prec, cx.x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, cx.an, s, mr1));
         h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
-        RUN(gemm(h, h->an, C, w.w1, C, 3, h->hbuf, true, C, C, w.b1, nullptr, kActNone, false, s));
+        RUN(conv3(cx.an, w.w1, cx.hb, w.b1, nullptr, false, NormFuse()));
     }
     {
         Stage t(h, "groupnorm_swish", s);
-        RUN(launch_groupnorm_stats(h->hbuf, rs, C, st2, s));
-        RUN(launch_groupnorm_apply_swish(prec, h->hbuf, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, h->an, s, mr2));
+        RUN(launch_groupnorm_stats(cx.hb, rs, C, st2, s));
+        RUN(launch_groupnorm_apply_swish(prec, cx.hb, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, cx.an, s, mr2));
         h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
-        RUN(gemm(h, h->an, C, w.w2, C, 3, h->x, true, C, C, w.b2, h->x, kActNone, false, s, nf));
+        RUN(conv3(cx.an, w.w2, cx.x, w.b2, cx.x, cx.mask_out, nf));
+    }
+    return 0;
+}
+
+int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t s,
+                 const NormFuse& nf = NormFuse()) {
+    ResCtx cx{&h->rs, h->C, h->x, h->hbuf, h->an, false};
+    return resnet_block_ex(h, cx, w, stats_slot, s, nf);
+}
+
+// UpSamplerBlock.forward (upsampler.py:62-69): per stage, ConvTranspose1d as `stride` row-shifted convs
+// (one per output phase, written with a row stride of `stride`), then a ResnetBlock; finally
+// out_proj + swish. Input: LayerNorm output h->an (halo rows zero); output: h->u_fin.
+int upsample_path(B200Codec* h, cudaStream_t s) {
+    const int prec = h->cfg.precision;
+    const void* cur = h->an;
+    const RowSpace* rs_in = &h->rs;
+    for (int i = 0; i < h->n_up; ++i) {
+        const UpStageW& st = h->up[i];
+        const RowSpace& rs_out = h->rs_up[i];
+        {
+            Stage t(h, "upsample_convT_gemm", s);
+            for (int ph = 0; ph < st.stride; ++ph) {
+                GemmCall c;
+                c.precision = prec;
+                c.a = cur;
+                c.a_rows = rs_in->rows;
+                c.Cin = st.Cin;
+                c.w = st.phase[ph].w;
+                c.N = st.Cout;
+                c.taps = st.phase[ph].taps;
+                c.tap_pad = st.phase[ph].pad;
+                c.out = h->u_x[i] + static_cast<size_t>(ph) * st.Cout;  // out row = stride * m + ph
+                c.out_fp32 = 1;
+                c.ldc = st.stride * st.Cout;
+                c.n_store = st.Cout;
+                c.bias = st.bias;
+                c.residual = nullptr;
+                c.ld_res = 0;
+                c.row_valid = nullptr;
+                c.act = kActNone;
+                RUN(launch_gemm(c, s));
+            }
+        }
+        NormFuse nf;
+        nf.out16 = h->u_a16[i];  // operand copy of the block output: input of the next stage / out_proj
+        ResCtx cx{&rs_out, st.Cout, h->u_x[i], h->u_h[i], h->u_an[i], true};
+        if (resnet_block_ex(h, cx, st.res, 8 + 2 * i, s, nf)) return 1;
+        cur = h->u_a16[i];
+        rs_in = &rs_out;
+    }
+    {
+        Stage t(h, "out_proj_gemm", s);
+        GemmCall c;
+        c.precision = prec;
+        c.a = cur;
+        c.a_rows = rs_in->rows;
+        c.Cin = h->C >> h->n_up;
+        c.w = h->w_out_proj;
+        c.N = h->C;
+        c.taps = 1;
+        c.out = h->u_fin;
+        c.out_fp32 = 0;
+        c.ldc = h->C;
+        c.n_store = h->C;
+        c.bias = h->m("upsampler.out_proj.bias");
+        c.residual = nullptr;
+        c.ld_res = 0;
+        c.row_valid = nullptr;
+        c.act = kActSilu;  // nonlinearity(out_proj(x)) (upsampler.py:69)
+        RUN(launch_gemm(c, s));
     }
     return 0;
 }
@@ -532,7 +732,7 @@ int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cuda
 int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s) {
     const int C = h->C, prec = h->cfg.precision;
     const RowSpace& rs = h->rs;
-    B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * 8 * rs.n_utts * 64, s));
+    B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * h->gn_slots * rs.n_utts * 64, s));
     {
         Stage t(h, "fsq_lookup", s);
         RUN(launch_fsq_lookup(ids_dev, id_type, rs.row_tok, rs.rows,
@@ -604,21 +804,44 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
     if (resnet_block(h, h->res[3], 6, s)) return 1;
     {
         Stage t(h, "layernorm", s);
+        // with an upsampler the LayerNorm output feeds a transposed conv: halo rows must be zero
         RUN(launch_layernorm(prec, h->x, h->m("decoder.backbone.final_layer_norm.weight"),
                              h->m("decoder.backbone.final_layer_norm.bias"), rs.rows, C, 1e-6f,
-                             h->an, s));
+                             h->an, s, h->n_up > 0 ? rs.row_valid : nullptr));
+    }
+    const RowSpace& rs_last = h->n_up > 0 ? h->rs_up[h->n_up - 1] : rs;
+    const void* head_in = h->an;
+    if (h->n_up > 0) {
+        if (upsample_path(h, s)) return 1;
+        head_in = h->u_fin;
     }
     {
         Stage t(h, "head_gemm", s);
-        RUN(gemm(h, h->an, C, h->w_head, h->n_fft + 2, 1, h->ho, true, kHeadLd, kHeadLd,
-                 h->head_bias_pad, nullptr, kActNone, false, s));
+        GemmCall c;
+        c.precision = prec;
+        c.a = head_in;
+        c.a_rows = rs_last.rows;
+        c.Cin = C;
+        c.w = h->w_head;
+        c.N = h->n_fft + 2;
+        c.taps = 1;
+        c.out = h->ho;
+        c.out_fp32 = 1;
+        c.ldc = h->head_ld;
+        c.n_store = h->head_ld;
+        c.bias = h->head_bias_pad;
+        c.residual = nullptr;
+        c.ld_res = 0;
+        c.row_valid = nullptr;
+        c.act = kActNone;
+        RUN(launch_gemm(c, s));
     }
     {
         Stage t(h, "istft", s);
         IstftTables tab;
         tab.twiddle = h->twiddle;
         tab.window = h->m("decoder.head.istft.window");
-        RUN(launch_istft(h->ho, kHeadLd, rs, tab, h->hop, wav_dev, s));
+        RUN(launch_istft(h->ho, h->head_ld, rs_last, tab, h->hop, wav_dev, s));
     }
     return 0;
 }
@@ -662,13 +885,22 @@ int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
     B200_CHECK(cfg != nullptr && out != nullptr, "b200codec_create: null argument");
     B200_CHECK(cfg->abi_version == B200CODEC_ABI_VERSION, "ABI version mismatch: caller %d, library %d",
                cfg->abi_version, B200CODEC_ABI_VERSION);
-    B200_CHECK(cfg->n_upsample == 0,
-               "upsample_factors are not supported yet: the 48 kHz UpSamplerBlock variant "
-               "(tts/core/codec/upsampler.py) is a NEXT row (SURVEY.md 8f-1)");
-    B200_CHECK(cfg->hop_length > 0 && cfg->sample_rate / cfg->hop_length == 50,
-               "Current hop length %d and upsample factors None do not match the target sample "
-               "rate %d.", cfg->hop_length, cfg->sample_rate);  // decoder.py:31-37
-    B200_CHECK(cfg->hop_length == 320, "only hop_length == 320 (xcodec2, 16 kHz) is instantiated");
+    B200_CHECK(cfg->n_upsample >= 0 && cfg->n_upsample <= 2,
+               "upsample_factors: %d stages are not supported (0, 1 or 2; channels halve per stage and the "
+               "kernels are instantiated for 512 and 256)", cfg->n_upsample);
+    int total_up = 1;
+    for (int i = 0; i < cfg->n_upsample; ++i) {
+        const int u = cfg->upsample_factors[i], k = cfg->kernel_sizes[i];
+        B200_CHECK(u >= 1 && u <= 8 && k >= u && k <= 16 && (k - u) % 2 == 0,
+                   "unsupported upsampler stage %d: factor %d kernel %d (need factor <= kernel, kernel - factor even)",
+                   i, u, k);
+        total_up *= u;
+    }
+    B200_CHECK(cfg->hop_length > 0 && cfg->sample_rate / cfg->hop_length / total_up == 50,
+               "Current hop length %d and upsample factors (product %d) do not match the target sample "
+               "rate %d.", cfg->hop_length, total_up, cfg->sample_rate);  // decoder.py:31-37
+    B200_CHECK(cfg->hop_length == 320 || cfg->hop_length == 160,
+               "only hop_length 320 (n_fft 1280) and 160 (n_fft 640) are instantiated");
     B200_CHECK(cfg->precision == B200CODEC_BF16 || cfg->precision == B200CODEC_FP16,
                "precision %d is not available (bf16 = 0, fp16 = 1)", cfg->precision);
     B200_CHECK(cfg->hidden_dim == 1024 && cfg->heads == 16 && cfg->vq_dim == 2048 &&
@@ -694,6 +926,18 @@ int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
     h->hop = cfg->hop_length;
     h->n_fft = 4 * cfg->hop_length;
     h->n_bins = h->n_fft / 2 + 1;
+    h->head_ld = (h->n_fft + 2 + 31) / 32 * 32;
+    h->n_up = cfg->n_upsample;
+    h->total_up = total_up;
+    h->gn_slots = 8 + 2 * h->n_up;
+    for (int i = 0; i < h->n_up; ++i) {
+        h->up_f[i] = cfg->upsample_factors[i];
+        h->up_k[i] = cfg->kernel_sizes[i];
+        h->up[i].Cin = h->C >> i;
+        h->up[i].Cout = h->C >> (i + 1);
+        h->up[i].stride = h->up_f[i];
+        h->up[i].k = h->up_k[i];
+    }
     build_specs(h);
     h->master.assign(h->specs.size(), nullptr);
     if (cudaHostAlloc(reinterpret_cast<void**>(&h->err_flag_host), sizeof(int),
@@ -730,6 +974,7 @@ void b200codec_destroy(B200Codec* h) {
     h->wbuf.release();
     h->ws.release();
     h->plan_dev.release();
+    for (int i = 0; i < kMaxUp; ++i) h->plan_up_dev[i].release();
     h->io_ids.release();
     h->io_wav.release();
     if (h->plan_host) cudaFreeHost(h->plan_host);
@@ -827,6 +1072,11 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     size_t elems = static_cast<size_t>(C) * V + static_cast<size_t>(C) * C * 7 +
                    8 * static_cast<size_t>(C) * C * 3 +
                    static_cast<size_t>(L) * (3ull * C * C + 1ull * C * C + 8ull * C * C) + n_head;
+    for (int i = 0; i < h->n_up; ++i) {
+        const size_t ci = h->up[i].Cin, co = h->up[i].Cout;
+        elems += ci * co * (h->up[i].k + h->up[i].stride * 2) + 2 * co * co * 3 + 4096;
+    }
+    if (h->n_up > 0) elems += static_cast<size_t>(C) * (C >> h->n_up) + 4096;
     if (h->wbuf.ensure(elems * es + 64 * 1024)) return 1;
     uint8_t* wp = h->wbuf.as<uint8_t>();
     auto take = [&](size_t n) {
@@ -894,11 +1144,59 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
         if (launch_repack_weight(prec, h->m(p + "mlp.fc1.weight"), w.fc1, 4 * C, C, 1, s, w.ffn_norm)) return 1;
         if (launch_repack_weight(prec, h->m(p + "mlp.fc2.weight"), w.fc2, C, 4 * C, 1, s)) return 1;
     }
+    // ---- upsampler (48 kHz variant): weight-norm fold + one K-major slab set per output phase ----
+    // ConvTranspose1d(stride u, kernel k, padding p = (k - u) / 2): out[u q + ph] = sum_e x[q + e] W[:, :, ph + p - u e]
+    // over the e with 0 <= ph + p - u e < k, i.e. an ordinary conv over consecutive input rows per phase.
+    float* wn_scale = nullptr;
+    if (h->n_up > 0) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&wn_scale), C * sizeof(float)));
+    for (int i = 0; i < h->n_up; ++i) {
+        UpStageW& st = h->up[i];
+        const std::string pl = "upsampler.upsample_layers." + std::to_string(i) + ".";
+        const std::string pr = "upsampler.resnet_blocks." + std::to_string(i) + ".";
+        const int u = st.stride, k = st.k, pad = (k - u) / 2;
+        st.bias = h->m(pl + "bias");
+        if (launch_weightnorm_scale(h->m(pl + "weight_g"), h->m(pl + "weight_v"), st.Cin, st.Cout * k, wn_scale, s)) return 1;
+        for (int ph = 0; ph < u; ++ph) {
+            int e_min = 1 << 20, e_max = -(1 << 20);
+            for (int e = -16; e <= 16; ++e) {
+                const int tap = ph + pad - u * e;
+                if (tap >= 0 && tap < k) {
+                    e_min = e < e_min ? e : e_min;
+                    e_max = e > e_max ? e : e_max;
+                }
+            }
+            B200_CHECK(e_min <= e_max && e_min <= 0 && e_max - e_min + 1 <= 8, "upsampler stage %d phase %d has no taps", i, ph);
+            int tap_ids[8] = {0};
+            const int taps = e_max - e_min + 1;
+            for (int t = 0; t < taps; ++t) tap_ids[t] = ph + pad - u * (e_min + t);
+            st.phase[ph].taps = taps;
+            st.phase[ph].pad = -e_min;
+            st.phase[ph].w = take(static_cast<size_t>(st.Cout) * taps * st.Cin);
+            if (launch_repack_convT_phase(prec, h->m(pl + "weight_v"), wn_scale, st.phase[ph].w, st.Cin, st.Cout, k,
+                                          taps, tap_ids, s))
+                return 1;
+        }
+        ResBlockW& r = st.res;
+        r.gn1_w = h->m(pr + "norm1.weight");
+        r.gn1_b = h->m(pr + "norm1.bias");
+        r.b1 = h->m(pr + "conv1.bias");
+        r.gn2_w = h->m(pr + "norm2.weight");
+        r.gn2_b = h->m(pr + "norm2.bias");
+        r.b2 = h->m(pr + "conv2.bias");
+        r.w1 = take(static_cast<size_t>(st.Cout) * st.Cout * 3);
+        r.w2 = take(static_cast<size_t>(st.Cout) * st.Cout * 3);
+        if (launch_repack_weight(prec, h->m(pr + "conv1.weight"), r.w1, st.Cout, st.Cout, 3, s)) return 1;
+        if (launch_repack_weight(prec, h->m(pr + "conv2.weight"), r.w2, st.Cout, st.Cout, 3, s)) return 1;
+    }
+    if (h->n_up > 0) {
+        h->w_out_proj = take(static_cast<size_t>(C) * (C >> h->n_up));
+        if (launch_repack_weight(prec, h->m("upsampler.out_proj.weight"), h->w_out_proj, C, C >> h->n_up, 1, s)) return 1;
+    }
     h->w_head = take(n_head);
     if (launch_repack_weight(prec, h->m("decoder.head.out.weight"), h->w_head, h->n_fft + 2, C, 1, s)) return 1;
     if (!h->head_bias_pad)
-        B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->head_bias_pad), kHeadLd * sizeof(float)));
-    B200_CUDA_OK(cudaMemsetAsync(h->head_bias_pad, 0, kHeadLd * sizeof(float), s));
+        B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->head_bias_pad), h->head_ld * sizeof(float)));
+    B200_CUDA_OK(cudaMemsetAsync(h->head_bias_pad, 0, h->head_ld * sizeof(float), s));
     B200_CUDA_OK(cudaMemcpyAsync(h->head_bias_pad, h->m("decoder.head.out.bias"),
                                  (h->n_fft + 2) * sizeof(float), cudaMemcpyDeviceToDevice, s));
     {
@@ -912,6 +1210,7 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     }
     B200_CUDA_OK(cudaStreamSynchronize(s));
     B200_CUDA_OK(cudaFree(scratch));
+    if (wn_scale) B200_CUDA_OK(cudaFree(wn_scale));
     h->finalized = true;
     return 0;
 }
@@ -923,8 +1222,8 @@ int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
     B200_CHECK(ids_dev && wav_dev, "decode: null device buffer");
     // 8 GroupNorm layers x [n_utts][32 groups][sum, sumsq] fp64
     // + one float2 [n_utts][32] (mean, rstd) scratch per GroupNorm layer
-    const size_t need = sizeof(double) * 8 * static_cast<size_t>(n_utts) * 64 +
-                        sizeof(float2) * 8 * static_cast<size_t>(n_utts) * 32;
+    const size_t need = sizeof(double) * h->gn_slots * static_cast<size_t>(n_utts) * 64 +
+                        sizeof(float2) * h->gn_slots * static_cast<size_t>(n_utts) * 32;
     if (h->gn_stats_bytes < need) {
         if (h->gn_stats) B200_CUDA_OK(cudaFree(h->gn_stats));
         h->gn_stats = nullptr;
@@ -960,7 +1259,7 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
     if (check_ids_host(ids_host, id_type, toks)) return 1;
     B200_CUDA_OK(cudaSetDevice(h->cfg.device));
     const size_t id_bytes = static_cast<size_t>(toks) * (id_type == B200CODEC_IDS_I64 ? 8 : 4);
-    const size_t wav_bytes = static_cast<size_t>(toks) * h->hop * sizeof(float);
+    const size_t wav_bytes = static_cast<size_t>(toks) * h->hop * h->total_up * sizeof(float);
     if (h->io_ids.ensure(id_bytes)) return 1;
     if (h->io_wav.ensure(wav_bytes)) return 1;
     B200_CUDA_OK(cudaMemcpyAsync(h->io_ids.p, ids_host, id_bytes, cudaMemcpyHostToDevice, s));
@@ -970,6 +1269,8 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }
+
+int b200codec_samples_per_token(const B200Codec* h) { return h ? h->hop * h->total_up : 0; }
 
 int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0; }
 

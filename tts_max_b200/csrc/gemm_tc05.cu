@@ -63,6 +63,44 @@ __global__ void fold_rope_kernel(float* __restrict__ w, int heads, int head_dim,
     }
 }
 
+__global__ void weightnorm_scale_kernel(const float* __restrict__ g, const float* __restrict__ v, int inner,
+                                        float* __restrict__ scale) {
+    const int c = blockIdx.x;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+        const float x = v[static_cast<size_t>(c) * inner + i];
+        ss = fmaf(x, x, ss);
+    }
+    __shared__ float red[32];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) scale[c] = g[c] / sqrtf(t);
+    }
+}
+
+struct TapIds {
+    int id[8];
+};
+
+template <typename T>
+__global__ void repack_convT_phase_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+                                          T* __restrict__ dst, int Cin, int Cout, int k, int taps, TapIds ids) {
+    const size_t total = static_cast<size_t>(Cout) * taps * Cin;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        const size_t rest = i / Cin;
+        const int t = static_cast<int>(rest % taps);
+        const size_t co = rest / taps;
+        const float x = v[(static_cast<size_t>(ci) * Cout + co) * k + ids.id[t]] * scale[ci];
+        dst[i] = Half16<T>::from_float(x);
+    }
+}
+
 template <typename InT>
 int dispatch(const GemmCall& c, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
              bool wide, cudaStream_t stream) {
@@ -141,7 +179,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     B200_CHECK(c.Cin % block_k == 0, "gemm: Cin (%d) must be a multiple of %d", c.Cin, block_k);
     B200_CHECK(c.n_store % 32 == 0 && c.n_store <= c.ldc, "gemm: bad n_store %d (ldc %d)",
                c.n_store, c.ldc);
-    B200_CHECK(c.taps >= 1 && c.taps % 2 == 1, "gemm: taps must be odd");
+    B200_CHECK(c.taps >= 1 && (c.tap_pad >= 0 || c.taps % 2 == 1), "gemm: even tap counts need an explicit tap_pad");
     B200_CHECK(c.residual == nullptr || c.out_fp32, "gemm: a residual requires fp32 output");
     if (c.a_rows <= 0) return 0;
     const bool wide = gemm_is_wide(c);
@@ -154,7 +192,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     p.n_store = c.n_store;
     p.k_blocks_per_tap = c.Cin / block_k;
     p.taps = c.taps;
-    p.tap_pad = c.taps / 2;
+    p.tap_pad = c.tap_pad >= 0 ? c.tap_pad : c.taps / 2;
     p.out = c.out;
     p.ldc = c.ldc;
     p.bias = c.bias;
@@ -171,8 +209,9 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     const bool fused = c.ss_in != nullptr || c.out16 != nullptr || c.ss_out != nullptr;
     B200_CHECK(!fused || gemm_kind(c) == kGemm2Cta,
                "gemm: the RMSNorm-fused epilogue needs the CTA-pair kernel (N % 256 == 0)");
-    B200_CHECK((c.out16 == nullptr && c.ss_out == nullptr) || (c.out_fp32 && c.n_store == 1024),
-               "gemm: out16 / ss_out require fp32 output with N == 1024");
+    B200_CHECK(c.out16 == nullptr || c.out_fp32, "gemm: out16 requires fp32 output");
+    B200_CHECK(c.ss_out == nullptr || (c.out_fp32 && c.n_store == 1024),
+               "gemm: ss_out requires fp32 output with N == 1024");
     if (gemm_kind(c) == kGemm2Cta) {
         if (c.precision == kPrecBf16)
             return c.out_fp32 ? launch_gemm_tc05_2cta<__nv_bfloat16, float>(ta, tb, p, stream)
@@ -197,6 +236,33 @@ int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, 
                                                                Cin, taps, col_scale);
     else {
         set_error("repack: unsupported precision %d", prec);
+        return 1;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_weightnorm_scale(const float* g, const float* v, int C0, int inner, float* scale, cudaStream_t stream) {
+    weightnorm_scale_kernel<<<C0, 256, 0, stream>>>(g, v, inner, scale);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_repack_convT_phase(int prec, const float* v, const float* scale, void* dst, int Cin, int Cout, int k,
+                              int taps, const int* tap_ids, cudaStream_t stream) {
+    B200_CHECK(taps >= 1 && taps <= 8, "convT repack: bad tap count %d", taps);
+    TapIds ids;
+    for (int t = 0; t < 8; ++t) ids.id[t] = t < taps ? tap_ids[t] : 0;
+    const size_t total = static_cast<size_t>(Cout) * taps * Cin;
+    const int grid = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    if (prec == kPrecBf16)
+        repack_convT_phase_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(v, scale, static_cast<__nv_bfloat16*>(dst),
+                                                                           Cin, Cout, k, taps, ids);
+    else if (prec == kPrecFp16)
+        repack_convT_phase_kernel<__half><<<grid, 256, 0, stream>>>(v, scale, static_cast<__half*>(dst), Cin, Cout, k,
+                                                                    taps, ids);
+    else {
+        set_error("convT repack: unsupported precision %d", prec);
         return 1;
     }
     B200_CUDA_OK(cudaGetLastError());

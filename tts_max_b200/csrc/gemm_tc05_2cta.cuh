@@ -342,6 +342,8 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 o.y += res[cur][i].y;
                                 o.z += res[cur][i].z;
                                 o.w += res[cur][i].w;
+                                // halo rows stay zero even when a residual is added
+                                if (p.row_valid != nullptr && p.row_valid[grow] == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
                             *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldc + n0 + sub_w) = o;
                             // fused RMSNorm, producer side: 16-bit copy + row sum of squares

@@ -24,31 +24,33 @@ namespace b200 {
 
 namespace {
 
-constexpr int kHop = 320;
-constexpr int kNfft = 1280;
-constexpr int kHalf = 640;   // complex FFT length
-constexpr int kBins = 641;
 constexpr int kGroup = 4;    // frames transformed together
 constexpr int kIstftThreads = 256;
 constexpr int kTileFrames = kIstftOutHops + 4;
 static_assert(kTileFrames % kGroup == 0, "tile frames must be a multiple of the group");
 
+// HOP = 320 (xcodec2, 16 kHz: n_fft 1280, complex FFT 640 = 4*4*4*10) or 160 (48 kHz upsampler
+// variant: n_fft 640, complex FFT 320 = 4*4*4*5)
+template <int HOP>
 struct IstftSmem {
+    static constexpr int kNfft = 4 * HOP;
+    static constexpr int kHalf = 2 * HOP;
     float2 buf_a[kGroup][kHalf];
     float2 buf_b[kGroup][kHalf];
     float2 tw[kNfft];
     float win[kNfft];
-    float ola[kIstftOutHops * kHop];
+    float ola[kIstftOutHops * HOP];
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// one Stockham pass of radix R over `kGroup` independent length-640 transforms
-template <int R>
+// one Stockham pass of radix R over `kGroup` independent length-kHalf transforms
+template <int R, int kHalf>
 __device__ __forceinline__ void stockham_pass(const float2 (*src)[kHalf], float2 (*dst)[kHalf],
                                               const float2* tw, int Ns) {
+    constexpr int kNfft = 2 * kHalf;
     constexpr int kButterflies = kHalf / R;
     const int tw_stride = kNfft / (Ns * R);
     for (int idx = threadIdx.x; idx < kGroup * kButterflies; idx += kIstftThreads) {
@@ -73,8 +75,30 @@ __device__ __forceinline__ void stockham_pass(const float2 (*src)[kHalf], float2
             dst[f][j0 + 1 * Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
             dst[f][j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
             dst[f][j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+        } else if constexpr (R == 5) {
+            // inverse DFT-5: X_k = sum_n x_n exp(+2 pi i n k / 5)
+            constexpr float c1 = 0.30901699437494745f;   // cos(2 pi / 5)
+            constexpr float c2 = -0.8090169943749475f;   // cos(4 pi / 5)
+            constexpr float s1 = 0.9510565162951535f;    // sin(2 pi / 5)
+            constexpr float s2 = 0.5877852522924731f;    // sin(4 pi / 5)
+            const float2 x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3], x4 = v[4];
+            const float2 a1 = make_float2(x1.x + x4.x, x1.y + x4.y);
+            const float2 a2 = make_float2(x2.x + x3.x, x2.y + x3.y);
+            const float2 b1 = make_float2(x1.x - x4.x, x1.y - x4.y);
+            const float2 b2 = make_float2(x2.x - x3.x, x2.y - x3.y);
+            const float2 e1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+            const float2 e2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+            const float2 t1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+            const float2 t2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+            const float2 d1 = make_float2(-t1.y, t1.x);  // i * t1
+            const float2 d2 = make_float2(-t2.y, t2.x);
+            dst[f][j0 + 0 * Ns] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
+            dst[f][j0 + 1 * Ns] = make_float2(e1.x + d1.x, e1.y + d1.y);
+            dst[f][j0 + 4 * Ns] = make_float2(e1.x - d1.x, e1.y - d1.y);
+            dst[f][j0 + 2 * Ns] = make_float2(e2.x + d2.x, e2.y + d2.y);
+            dst[f][j0 + 3 * Ns] = make_float2(e2.x - d2.x, e2.y - d2.y);
         } else {
-            static_assert(R == 10, "only radix 4 and 10 are instantiated");
+            static_assert(R == 10, "only radix 4, 5 and 10 are instantiated");
             // inverse DFT-10 by the prime-factor map (no inner twiddles): n = (5 n1 + 2 n2) % 10,
             // k = (5 k1 + 6 k2) % 10; two DFT-5 over n2, then five DFT-2 over n1.
             constexpr float c1 = 0.30901699437494745f;   // cos(2 pi / 5)
@@ -113,6 +137,7 @@ __device__ __forceinline__ void stockham_pass(const float2 (*src)[kHalf], float2
     }
 }
 
+template <int HOP>
 __global__ void __launch_bounds__(kIstftThreads)
 istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ work,
              const int32_t* __restrict__ utt_row0, const int32_t* __restrict__ utt_len,
@@ -120,8 +145,13 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
              const float* __restrict__ window, float* __restrict__ wav) {
     pdl_launch_dependents();
     pdl_wait();
+    constexpr int kHop = HOP;
+    constexpr int kNfft = 4 * HOP;
+    constexpr int kHalf = 2 * HOP;
+    constexpr int kBins = kHalf + 1;
+    constexpr int kPad = (kNfft - kHop) / 2;  // "same" trim on each side
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
+    IstftSmem<HOP>& sm = *reinterpret_cast<IstftSmem<HOP>*>(smem_raw);
 
     const int4 wk = work[blockIdx.x];
     const int utt = wk.x, b0 = wk.y;
@@ -185,13 +215,13 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
         __syncthreads();
 
         // 3. length-640 inverse complex FFT, radix 4-4-4-10, ping-pong a -> b -> a -> b -> a
-        stockham_pass<4>(sm.buf_a, sm.buf_b, sm.tw, 1);
+        stockham_pass<4, kHalf>(sm.buf_a, sm.buf_b, sm.tw, 1);
         __syncthreads();
-        stockham_pass<4>(sm.buf_b, sm.buf_a, sm.tw, 4);
+        stockham_pass<4, kHalf>(sm.buf_b, sm.buf_a, sm.tw, 4);
         __syncthreads();
-        stockham_pass<4>(sm.buf_a, sm.buf_b, sm.tw, 16);
+        stockham_pass<4, kHalf>(sm.buf_a, sm.buf_b, sm.tw, 16);
         __syncthreads();
-        stockham_pass<10>(sm.buf_b, sm.buf_a, sm.tw, 64);
+        stockham_pass<kHalf / 64, kHalf>(sm.buf_b, sm.buf_a, sm.tw, 64);  // radix 10 (640) or 5 (320)
         __syncthreads();
 
         // 4. window, 1/n_fft and overlap-add (gather form: one thread per output sample).
@@ -202,7 +232,7 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
             for (int f = 0; f < kGroup; ++f) {
                 const int t = t_first + f;
                 // frame t covers output samples [320 t - 480, 320 t + 800); n is relative to 320 b0
-                const int m = n + 480 - kHop * (t - b0);
+                const int m = n + kPad - kHop * (t - b0);
                 if (t >= 0 && t < T && m >= 0 && m < kNfft)
                     acc += reinterpret_cast<const float*>(sm.buf_a[f])[m] * (1.f / kNfft) * sm.win[m];
             }
@@ -219,33 +249,39 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
 #pragma unroll
         for (int dt = -2; dt <= 2; ++dt) {
             const int t = b + dt;
-            const int m = n + 480 - kHop * (t - b0);
+            const int m = n + kPad - kHop * (t - b0);
             if (t >= 0 && t < T && m >= 0 && m < kNfft) env = fmaf(sm.win[m], sm.win[m], env);
         }
         wav_u[static_cast<size_t>(b0) * kHop + n] = sm.ola[n] / env;
     }
 }
 
+template <int HOP>
+int launch_istft_typed(const float* x_pred, int ld, const RowSpace& rs, const IstftTables& tab, float* wav,
+                       cudaStream_t stream) {
+    B200_CHECK(ld >= 2 * (2 * HOP + 1), "istft: ld %d < %d", ld, 2 * (2 * HOP + 1));
+    static PerDeviceOnce once;
+    if (once.need()) {
+        B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(IstftSmem<HOP>))));
+        B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel<HOP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+    }
+    B200_CUDA_OK(launch_kernel(istft_kernel<HOP>, dim3(rs.n_istft_work), dim3(kIstftThreads),
+                               sizeof(IstftSmem<HOP>), stream, x_pred, ld, rs.istft_work, rs.utt_row0, rs.utt_len,
+                               rs.utt_tok0, tab.twiddle, tab.window, wav));
+    return 0;
+}
+
 }  // namespace
 
 int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTables& tab, int hop,
                  float* wav, cudaStream_t stream) {
-    B200_CHECK(hop == kHop, "istft: only hop_length == 320 (n_fft 1280) is instantiated (got %d)",
-               hop);
-    B200_CHECK(ld >= 2 * kBins, "istft: ld %d < %d", ld, 2 * kBins);
     if (rs.n_istft_work <= 0) return 0;
-    static PerDeviceOnce once;
-    if (once.need()) {
-        B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(IstftSmem))));
-        B200_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
-    }
-    B200_CUDA_OK(launch_kernel(istft_kernel, dim3(rs.n_istft_work), dim3(kIstftThreads), sizeof(IstftSmem), stream,
-                               x_pred, ld, rs.istft_work, rs.utt_row0, rs.utt_len, rs.utt_tok0, tab.twiddle,
-                               tab.window, wav));
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    if (hop == 320) return launch_istft_typed<320>(x_pred, ld, rs, tab, wav, stream);
+    if (hop == 160) return launch_istft_typed<160>(x_pred, ld, rs, tab, wav, stream);
+    set_error("istft: hop_length %d is not instantiated (320: n_fft 1280, 160: n_fft 640)", hop);
+    return 1;
 }
 
 }  // namespace b200

@@ -49,8 +49,9 @@ int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int 
 // w == nullptr: no elementwise weight (it is folded into the consumer GEMM's weight columns)
 int launch_rmsnorm(int prec, const float* x, const float* w, int rows, int dim, float eps,
                    void* out, cudaStream_t stream);
+// row_valid (optional): rows flagged 0 are written as zeros (operand of a following conv)
 int launch_layernorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
-                     float eps, void* out, cudaStream_t stream);
+                     float eps, void* out, cudaStream_t stream, const uint8_t* row_valid = nullptr);
 // stats: double [n_utts][32][2] (sum, sumsq), must be zero on entry
 int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
                            cudaStream_t stream);
@@ -84,6 +85,7 @@ struct GemmCall {
     const void* w;       // [N, taps*Cin]
     int N;               // logical out features (rows of w)
     int taps;
+    int tap_pad = -1;    // A row = m + tap - tap_pad; -1 -> taps / 2 ("same" conv)
     void* out;
     int out_fp32;        // 1 -> fp32 output, 0 -> operand dtype (tf32 mode: always fp32 storage)
     int ldc;
@@ -117,6 +119,12 @@ int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out);
 // col_scale (optional, [Cin], taps == 1): dst[n, c] = src[n, c] * col_scale[c]  (norm weight fold)
 int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,
                          cudaStream_t stream, const float* col_scale = nullptr);
+// weight_norm (dim 0): scale[c] = g[c] / ||v[c, :]||_2 over the `inner` trailing elements
+int launch_weightnorm_scale(const float* g, const float* v, int C0, int inner, float* scale, cudaStream_t stream);
+// one ConvTranspose1d output phase: dst[co, t * Cin + ci] = v[ci, co, tap_ids[t]] * scale[ci]
+// (v is the torch ConvTranspose1d weight_v [Cin, Cout, k])
+int launch_repack_convT_phase(int prec, const float* v, const float* scale, void* dst, int Cin, int Cout, int k,
+                              int taps, const int* tap_ids, cudaStream_t stream);
 // in-place on fp32 c_attn weight [3*H*64, K]: rotate q,k row pairs by the head-indexed angle
 int launch_fold_rope(float* w_qkv, int heads, int head_dim, int K, const float* cos_tab,
                      const float* sin_tab, cudaStream_t stream);

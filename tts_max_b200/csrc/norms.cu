@@ -35,13 +35,21 @@ __device__ __forceinline__ void store8_out(OutT* dst, const float* v) {
 template <typename OutT, int kChunks, bool kLayerNorm>
 __global__ void __launch_bounds__(kNormWarps * 32)
 rownorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-               const float* __restrict__ b, int rows, float eps, OutT* __restrict__ out) {
+               const float* __restrict__ b, int rows, float eps, OutT* __restrict__ out,
+               const uint8_t* __restrict__ row_valid) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int dim = kChunks * 256;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kNormWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (row_valid != nullptr && row_valid[row] == 0) {  // halo row: zeros for the conv that follows
+        OutT* zrow = out + static_cast<size_t>(row) * dim;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i)
+            *reinterpret_cast<uint4*>(zrow + i * 256 + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
     const float* xr = x + static_cast<size_t>(row) * dim;
     float v[kChunks][8];
 #pragma unroll
@@ -98,16 +106,16 @@ rownorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
 
 template <bool kLayerNorm>
 int launch_rownorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
-                   float eps, void* out, cudaStream_t stream) {
+                   float eps, void* out, cudaStream_t stream, const uint8_t* row_valid) {
     B200_CHECK(dim == 1024, "row norm: only dim == 1024 is instantiated (got %d)", dim);
     if (rows <= 0) return 0;
     const int grid = (rows + kNormWarps - 1) / kNormWarps;
     if (prec == kPrecBf16)
         B200_CUDA_OK(launch_kernel(rownorm_kernel<__nv_bfloat16, 4, kLayerNorm>, dim3(grid), dim3(kNormWarps * 32), 0,
-                                   stream, x, w, b, rows, eps, static_cast<__nv_bfloat16*>(out)));
+                                   stream, x, w, b, rows, eps, static_cast<__nv_bfloat16*>(out), row_valid));
     else if (prec == kPrecFp16)
         B200_CUDA_OK(launch_kernel(rownorm_kernel<__half, 4, kLayerNorm>, dim3(grid), dim3(kNormWarps * 32), 0, stream,
-                                   x, w, b, rows, eps, static_cast<__half*>(out)));
+                                   x, w, b, rows, eps, static_cast<__half*>(out), row_valid));
     else {
         set_error("row norm: unsupported precision %d", prec);
         return 1;
@@ -126,22 +134,28 @@ constexpr int kGnRowsPerBlock = 16;
 // the attention tile list). The chunking is relative to the utterance start, so the fp32
 // partial sums -- and with them the whole decode -- do not depend on where in a batch the
 // utterance sits (row-of-batch == single decode).
+// DIM channels, 32 groups of DIM / 32 channels; a thread owns 4 channels, DIM / 4 threads cover a row,
+// a 256-thread CTA handles 1024 / DIM rows per step.
+template <int DIM>
 __global__ void __launch_bounds__(kGnThreads)
-groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ work, int dim,
+groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ work,
                        double* __restrict__ stats, const int32_t* __restrict__ row_utt) {
     pdl_launch_dependents();
     pdl_wait();
-    // dim == 1024: 32 channels per group == 8 consecutive threads
+    constexpr int kTpr = DIM / 4;            // threads per row
+    constexpr int kRows = kGnThreads / kTpr;  // rows per step
+    constexpr int kTpg = DIM / 32 / 4;        // threads per group (8, 4, 2)
     const int4 wk = work[blockIdx.x];
     const int t0 = wk.z + blockIdx.y * kGnRowsPerBlock;
     const int t1 = min(t0 + kGnRowsPerBlock, min(wk.z + kAttnBlockQ, wk.y));
     if (t0 >= t1) return;
     const int utt = row_utt[wk.x];
-    const int group = threadIdx.x >> 3;
+    const int tc = threadIdx.x % kTpr;  // channel thread
+    const int tr = threadIdx.x / kTpr;  // row slot
+    const int group = tc / kTpg;
     float s = 0.f, ss = 0.f;
-    for (int t = t0; t < t1; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(
-            x + static_cast<size_t>(wk.x + t) * dim + threadIdx.x * 4);
+    for (int t = t0 + tr; t < t1; t += kRows) {
+        const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(wk.x + t) * DIM + tc * 4);
         s += (v.x + v.y) + (v.z + v.w);
         ss = fmaf(v.x, v.x, ss);
         ss = fmaf(v.y, v.y, ss);
@@ -149,11 +163,11 @@ groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ wor
         ss = fmaf(v.w, v.w, ss);
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = kTpg / 2; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
     }
-    if ((threadIdx.x & 7) == 0) {
+    if ((tc % kTpg) == 0) {
         atomicAdd(stats + (static_cast<size_t>(utt) * 32 + group) * 2 + 0, static_cast<double>(s));
         atomicAdd(stats + (static_cast<size_t>(utt) * 32 + group) * 2 + 1, static_cast<double>(ss));
     }
@@ -175,20 +189,22 @@ __global__ void groupnorm_finalize_kernel(const double* __restrict__ stats,
 }
 
 // y = swish((x - mean) * rstd * gamma + beta) -> operand dtype; halo rows are written as zeros
-// (the conv that follows reads them as its padding). 128 threads per row, 8 channels per thread:
-// 2 x 128-bit loads, one 128-bit store; a 256-thread CTA streams two rows per iteration.
-template <typename OutT>
+// (the conv that follows reads them as its padding). DIM / 8 threads per row, 8 channels per thread:
+// 2 x 128-bit loads, one 128-bit store; a 256-thread CTA streams 2048 / DIM rows per iteration.
+template <typename OutT, int DIM>
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
-                             int rows, int dim, const float2* __restrict__ mean_rstd,
+                             int rows, const float2* __restrict__ mean_rstd,
                              const float* __restrict__ gamma, const float* __restrict__ beta,
                              OutT* __restrict__ out) {
     pdl_launch_dependents();
     pdl_wait();
-    const int t = threadIdx.x & 127;
-    const int sub = threadIdx.x >> 7;  // which of the two rows of an iteration
+    constexpr int kTpr = DIM / 8;             // threads per row (128, 64, 32)
+    constexpr int kRows = kGnThreads / kTpr;  // rows per iteration
+    const int t = threadIdx.x % kTpr;
+    const int sub = threadIdx.x / kTpr;
     const int c0 = t * 8;
-    const int group = t >> 2;          // 32 channels per group = 4 threads
+    const int group = c0 / (DIM / 32);  // a thread's 8 channels never straddle a group (group size >= 8)
     float g[8], b[8];
     {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
@@ -198,12 +214,12 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
         g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
         b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
     }
-    for (int r = blockIdx.x * 2 + sub; r < rows; r += gridDim.x * 2) {
+    for (int r = blockIdx.x * kRows + sub; r < rows; r += gridDim.x * kRows) {
         const int u = row_utt[r];
         uint4 packed = make_uint4(0u, 0u, 0u, 0u);
         if (u >= 0) {
             const float2 mr = __ldg(mean_rstd + u * 32 + group);
-            const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * dim + c0);
+            const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * DIM + c0);
             const float4 v0 = xp[0], v1 = xp[1];
             float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
@@ -216,7 +232,53 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
             packed.z = Half16<OutT>::pack(y[4], y[5]);
             packed.w = Half16<OutT>::pack(y[6], y[7]);
         }
-        *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * dim + c0) = packed;
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * DIM + c0) = packed;
+    }
+}
+
+template <int DIM>
+int launch_gn_typed(int prec, const float* x, const RowSpace& rs, const double* stats, const float* gamma,
+                    const float* beta, float eps, void* out, cudaStream_t stream, float2* mean_rstd,
+                    bool stats_only, double* stats_out) {
+    if (stats_only) {
+        if (rs.n_attn_work <= 0) return 0;
+        static_assert(kAttnBlockQ % kGnRowsPerBlock == 0, "GroupNorm chunks must tile the work item");
+        dim3 grid(rs.n_attn_work, kAttnBlockQ / kGnRowsPerBlock);
+        B200_CUDA_OK(launch_kernel(groupnorm_stats_kernel<DIM>, grid, dim3(kGnThreads), 0, stream, x,
+                                   rs.attn_work, stats_out, rs.row_utt));
+        return 0;
+    }
+    if (rs.rows <= 0) return 0;
+    B200_CUDA_OK(launch_kernel(groupnorm_finalize_kernel, dim3(rs.n_utts), dim3(32), 0, stream, stats, rs.utt_len,
+                               DIM / 32, eps, mean_rstd));
+    constexpr int kRows = kGnThreads / (DIM / 8);
+    int grid = (rs.rows + kRows - 1) / kRows;
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    if (prec == kPrecBf16)
+        B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__nv_bfloat16, DIM>, dim3(grid), dim3(kGnThreads), 0,
+                                   stream, x, rs.row_utt, rs.rows, static_cast<const float2*>(mean_rstd), gamma,
+                                   beta, static_cast<__nv_bfloat16*>(out)));
+    else if (prec == kPrecFp16)
+        B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__half, DIM>, dim3(grid), dim3(kGnThreads), 0, stream,
+                                   x, rs.row_utt, rs.rows, static_cast<const float2*>(mean_rstd), gamma, beta,
+                                   static_cast<__half*>(out)));
+    else {
+        set_error("groupnorm: unsupported precision %d", prec);
+        return 1;
+    }
+    return 0;
+}
+
+int launch_gn_dispatch(int dim, int prec, const float* x, const RowSpace& rs, const double* stats,
+                       const float* gamma, const float* beta, float eps, void* out, cudaStream_t stream,
+                       float2* mean_rstd, bool stats_only, double* stats_out) {
+    switch (dim) {
+        case 1024: return launch_gn_typed<1024>(prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, stats_only, stats_out);
+        case 512: return launch_gn_typed<512>(prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, stats_only, stats_out);
+        case 256: return launch_gn_typed<256>(prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, stats_only, stats_out);
+        default:
+            set_error("groupnorm: dim %d is not instantiated (1024, 512, 256)", dim);
+            return 1;
     }
 }
 
@@ -224,50 +286,24 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
 
 int launch_rmsnorm(int prec, const float* x, const float* w, int rows, int dim, float eps,
                    void* out, cudaStream_t stream) {
-    return launch_rownorm<false>(prec, x, w, nullptr, rows, dim, eps, out, stream);
+    return launch_rownorm<false>(prec, x, w, nullptr, rows, dim, eps, out, stream, nullptr);
 }
 
 int launch_layernorm(int prec, const float* x, const float* w, const float* b, int rows, int dim,
-                     float eps, void* out, cudaStream_t stream) {
-    return launch_rownorm<true>(prec, x, w, b, rows, dim, eps, out, stream);
+                     float eps, void* out, cudaStream_t stream, const uint8_t* row_valid) {
+    return launch_rownorm<true>(prec, x, w, b, rows, dim, eps, out, stream, row_valid);
 }
 
 int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
                            cudaStream_t stream) {
-    B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
-    if (rs.n_attn_work <= 0) return 0;
-    static_assert(kAttnBlockQ % kGnRowsPerBlock == 0, "GroupNorm chunks must tile the work item");
-    dim3 grid(rs.n_attn_work, kAttnBlockQ / kGnRowsPerBlock);
-    B200_CUDA_OK(launch_kernel(groupnorm_stats_kernel, grid, dim3(kGnThreads), 0, stream, x, rs.attn_work, dim, stats,
-                               rs.row_utt));
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_gn_dispatch(dim, kPrecBf16, x, rs, nullptr, nullptr, nullptr, 0.f, nullptr, stream, nullptr, true,
+                              stats);
 }
 
 int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, int dim,
                                  const double* stats, const float* gamma, const float* beta,
                                  float eps, void* out, cudaStream_t stream, float2* mean_rstd) {
-    B200_CHECK(dim == 1024, "groupnorm: only dim == 1024 is instantiated (got %d)", dim);
-    if (rs.rows <= 0) return 0;
-    B200_CUDA_OK(launch_kernel(groupnorm_finalize_kernel, dim3(rs.n_utts), dim3(32), 0, stream, stats, rs.utt_len,
-                               dim / 32, eps, mean_rstd));
-    B200_CUDA_OK(cudaGetLastError());
-    int grid = (rs.rows + 1) / 2;
-    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    if (prec == kPrecBf16)
-        B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__nv_bfloat16>, dim3(grid), dim3(kGnThreads), 0, stream,
-                                   x, rs.row_utt, rs.rows, dim, static_cast<const float2*>(mean_rstd), gamma, beta,
-                                   static_cast<__nv_bfloat16*>(out)));
-    else if (prec == kPrecFp16)
-        B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__half>, dim3(grid), dim3(kGnThreads), 0, stream, x,
-                                   rs.row_utt, rs.rows, dim, static_cast<const float2*>(mean_rstd), gamma, beta,
-                                   static_cast<__half*>(out)));
-    else {
-        set_error("groupnorm: unsupported precision %d", prec);
-        return 1;
-    }
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_gn_dispatch(dim, prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, false, nullptr);
 }
 
 }  // namespace b200
