@@ -173,3 +173,36 @@ def test_streaming_windows_config5(gpu_decoders, state_dict):
     wav = d(ids.cuda()).cpu()[:, 0, -16000:]
     ref = O.decoder_forward(state_dict, ids[:2])[:, 0, -16000:]
     check_wave(ref, wav[:2], "bf16", "config5 windows 0,1")
+
+
+def test_random_varlen_batches(gpu_decoders):
+    """Randomised shapes: many utterances of random length in one call; every waveform must equal its
+    single decode (batch invariance) and be finite."""
+    d = gpu_decoders["bf16"]
+    g = torch.Generator().manual_seed(2025)
+    for trial in range(3):
+        n = int(torch.randint(2, 40, (1,), generator=g))
+        lens = torch.randint(1, 400, (n,), generator=g).tolist()
+        utts = [torch.randint(0, 65536, (t,), generator=g) for t in lens]
+        packed = d.decode_packed_host(torch.cat(utts), lens)
+        assert packed.numel() == 320 * sum(lens) and torch.isfinite(packed).all()
+        offs = [0]
+        for t in lens:
+            offs.append(offs[-1] + t)
+        for k in sorted(set([0, n - 1, int(torch.randint(0, n, (1,), generator=g))])):
+            single = d.decode_packed_host(utts[k], [lens[k]])
+            got = packed[offs[k] * 320:offs[k + 1] * 320]
+            assert (got - single).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item()), (trial, k, lens[k])
+
+
+def test_many_short_utterances(gpu_decoders):
+    """300 one-to-three-token utterances in one call (plan arrays, per-utterance GroupNorm, tiny tiles)."""
+    d = gpu_decoders["bf16"]
+    g = torch.Generator().manual_seed(7)
+    lens = torch.randint(1, 4, (300,), generator=g).tolist()
+    utts = [torch.randint(0, 65536, (t,), generator=g) for t in lens]
+    packed = d.decode_packed_host(torch.cat(utts), lens)
+    assert torch.isfinite(packed).all()
+    single = d.decode_packed_host(utts[150], [lens[150]])
+    off = sum(lens[:150])
+    assert (packed[off * 320:(off + lens[150]) * 320] - single).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item())

@@ -926,7 +926,9 @@ int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
     h->hop = cfg->hop_length;
     h->n_fft = 4 * cfg->hop_length;
     h->n_bins = h->n_fft / 2 + 1;
-    h->head_ld = (h->n_fft + 2 + 31) / 32 * 32;
+    // head.out columns padded to a multiple of 256 (1282 -> 1536, 642 -> 768): the padded columns cost
+    // ~17 % extra MMA work but let the ragged GEMM run on the CTA-pair kernel
+    h->head_ld = (h->n_fft + 2 + 255) / 256 * 256;
     h->n_up = cfg->n_upsample;
     h->total_up = total_up;
     h->gn_slots = 8 + 2 * h->n_up;
