@@ -4,6 +4,8 @@
 
 #include <cudaTypedefs.h>
 
+#include <unordered_map>
+
 #include "kernels.h"
 
 namespace b200 {
@@ -114,8 +116,42 @@ int dispatch(const GemmCall& c, const CUtensorMap& ta, const CUtensorMap& tb, co
 
 }  // namespace
 
-int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
-                 uint64_t ld_elems, uint32_t box_rows) {
+namespace {
+struct TmapKey {
+    const void* base;
+    uint64_t rows, cols, ld;
+    uint32_t dtype, box_cols, box_rows;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && dtype == o.dtype &&
+               box_cols == o.box_cols && box_rows == o.box_rows;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        auto mix = [&h](uint64_t v) { h = (h ^ v) * 0x100000001B3ull + (h >> 29); };
+        mix(k.rows);
+        mix(k.cols);
+        mix(k.ld);
+        mix((static_cast<uint64_t>(k.dtype) << 40) | (static_cast<uint64_t>(k.box_cols) << 20) | k.box_rows);
+        return static_cast<size_t>(h);
+    }
+};
+struct alignas(64) TmapSlot {
+    CUtensorMap map;
+};
+}  // namespace
+
+int make_tmap_box(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                  uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows) {
+    // a tensor map is a pure function of the key (it holds the address, not the data)
+    static thread_local std::unordered_map<TmapKey, TmapSlot, TmapKeyHash> cache;
+    const TmapKey key{base, rows, cols, ld_elems, static_cast<uint32_t>(dtype), box_cols, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *map = it->second.map;
+        return 0;
+    }
     auto fn = get_encode_fn();
     B200_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     CUtensorMapDataType dt;
@@ -124,20 +160,35 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
         case kTmapBf16: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; esz = 2; break;
         case kTmapF16: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; esz = 2; break;
         case kTmapF32: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; esz = 4; break;
-        default: set_error("make_tmap_2d: bad dtype %d", dtype); return 1;
+        default: set_error("make_tmap_box: bad dtype %d", dtype); return 1;
+    }
+    CUtensorMapSwizzle swz;
+    switch (box_cols * esz) {
+        case 128: swz = CU_TENSOR_MAP_SWIZZLE_128B; break;
+        case 64: swz = CU_TENSOR_MAP_SWIZZLE_64B; break;
+        case 32: swz = CU_TENSOR_MAP_SWIZZLE_32B; break;
+        default: set_error("make_tmap_box: box row of %u bytes", (unsigned)(box_cols * esz)); return 1;
     }
     B200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
     B200_CHECK((ld_elems * esz) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
     B200_CHECK(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {ld_elems * esz};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    if (cache.size() >= 8192) cache.clear();  // shapes churn (varlen batches): bound the memo
+    cache[key].map = *map;
     return 0;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_rows) {
+    const uint32_t esz = dtype == kTmapF32 ? 4 : 2;
+    return make_tmap_box(map, base, dtype, rows, cols, ld_elems, 128 / esz, box_rows);
 }
 
 // kernel selection: CTA pairs (256x256 per cluster) whenever N tiles evenly -- for every M, so
@@ -171,6 +222,10 @@ int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out) {
         return 1;
     return 0;
 }
+
+#ifdef B200_GEMM_TRACE
+unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
+#endif
 
 int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     B200_CHECK(c.precision == kPrecBf16 || c.precision == kPrecFp16,
@@ -206,18 +261,37 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     p.out16 = c.out16;
     p.ld16 = c.ld16;
     p.ss_out = c.ss_out;
+#ifdef B200_GEMM_TRACE
+    p.trace = g_gemm_trace;
+#endif
     const bool fused = c.ss_in != nullptr || c.out16 != nullptr || c.ss_out != nullptr;
     B200_CHECK(!fused || gemm_kind(c) == kGemm2Cta,
                "gemm: the RMSNorm-fused epilogue needs the CTA-pair kernel (N % 256 == 0)");
     B200_CHECK(c.out16 == nullptr || c.out_fp32, "gemm: out16 requires fp32 output");
     B200_CHECK(c.ss_out == nullptr || (c.out_fp32 && c.n_store == 1024),
                "gemm: ss_out requires fp32 output with N == 1024");
+    B200_CHECK(c.residual == nullptr || gemm_kind(c) != kGemm2Cta ||
+                   ((reinterpret_cast<uintptr_t>(c.residual) & 31) == 0 && c.ld_res % 8 == 0),
+               "gemm: the residual must be 32-byte aligned with a row pitch that is a multiple of 8");
+    p.has32 = c.out_fp32 ? 1 : 0;
+    p.has16 = (!c.out_fp32 || c.out16 != nullptr) ? 1 : 0;
     if (gemm_kind(c) == kGemm2Cta) {
-        if (c.precision == kPrecBf16)
-            return c.out_fp32 ? launch_gemm_tc05_2cta<__nv_bfloat16, float>(ta, tb, p, stream)
-                              : launch_gemm_tc05_2cta<__nv_bfloat16, __nv_bfloat16>(ta, tb, p, stream);
-        return c.out_fp32 ? launch_gemm_tc05_2cta<__half, float>(ta, tb, p, stream)
-                          : launch_gemm_tc05_2cta<__half, __half>(ta, tb, p, stream);
+        // the epilogue stores with TMA: fp32 boxes of 32 x 32 (128-byte rows), 16-bit output
+        // (or operand copy) boxes of 32 x 32 (64-byte rows)
+        const int dt16 = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
+        alignas(64) CUtensorMap to32, to16;
+        to32 = ta;  // placeholders for the map this launch does not use
+        to16 = ta;
+        if (c.out_fp32) {
+            if (make_tmap_box(&to32, c.out, kTmapF32, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
+            if (c.out16 != nullptr &&
+                make_tmap_box(&to16, c.out16, dt16, c.a_rows, c.n_store, c.ld16, kGemm2ChunkCols, 32))
+                return 1;
+        } else {
+            if (make_tmap_box(&to16, c.out, dt16, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
+        }
+        if (c.precision == kPrecBf16) return launch_gemm_tc05_2cta<__nv_bfloat16>(ta, tb, to32, to16, p, stream);
+        return launch_gemm_tc05_2cta<__half>(ta, tb, to32, to16, p, stream);
     }
     if (c.precision == kPrecBf16) return dispatch<__nv_bfloat16>(c, ta, tb, p, wide, stream);
     return dispatch<__half>(c, ta, tb, p, wide, stream);

@@ -53,7 +53,27 @@ struct GemmParams {
     void* out16;           // [M, ld16] operand dtype or nullptr
     int ld16;
     float* ss_out;         // [M][8] or nullptr; slot = column / 128 (requires N == 1024)
+    // CTA-pair kernel: which outputs exist (their addresses travel in tensor maps)
+    int has32;             // fp32 `out` (+ optional residual)
+    int has16;             // 16-bit `out` (has32 == 0) or the 16-bit copy `out16` (has32 == 1)
+#ifdef B200_GEMM_TRACE
+    unsigned long long* trace;  // tools/gemm_trace.cu only: [gridDim.x][128] timestamps
+#endif
 };
+
+// in-kernel timeline for tools/gemm_trace.cu; compiles to nothing in the product build
+#ifdef B200_GEMM_TRACE
+#define B200_TRACE(slot)                                                                     \
+    do {                                                                                     \
+        if (p.trace != nullptr) {                                                            \
+            unsigned long long t_;                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                            \
+            p.trace[static_cast<size_t>(blockIdx.x) * 128 + (slot)] = t_;                     \
+        }                                                                                    \
+    } while (0)
+#else
+#define B200_TRACE(slot) do { } while (0)
+#endif
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmThreads = 256;
@@ -290,6 +310,11 @@ enum TmapDtype : int { kTmapBf16 = 0, kTmapF16 = 1, kTmapF32 = 2 };
 // and the 128-byte swizzle. Returns 0 on success.
 int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows);
+// General form: a {box_cols elements, box_rows} box whose row is 32, 64 or 128 bytes, swizzled
+// with the pattern of the same width. Encodings are memoised per thread (the decoder re-issues
+// the same few hundred maps every step; cuTensorMapEncodeTiled costs about a microsecond).
+int make_tmap_box(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                  uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);
 
 template <int BLOCK_N, typename InT, typename OutT, int kStages>
 int launch_gemm_tc05(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,

@@ -9,12 +9,21 @@
 // B tile (128 of the 256 weight rows), the tensor cores read the other half from the peer's
 // shared memory. Per SM that is 64 B/clk read + 64 B/clk written, and 1.5x fewer L2->SM bytes.
 //
-//   cluster (2 CTAs) tile: 256 (M) x 256 (N), K-step 64; 6-stage TMA ring of 32 KB per CTA
+//   cluster (2 CTAs) tile: 256 (M) x 256 (N), K-step 64; 5-stage TMA ring of 32 KB per CTA
 //   warp 0      TMA producer (both CTAs; loads signal the LEADER CTA's full barrier)
 //   warp 1      MMA issuer   (leader CTA only; commits multicast to both CTAs' barriers)
 //   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, both CTAs)
-//   warps 4-11  epilogue: 2 warps per TMEM lane quarter, each owning 128 of the 256 columns;
-//               the fp32 residual and the next TMEM chunk are prefetched one chunk ahead.
+//   warps 4-11  epilogue: 2 warps per TMEM lane quarter, each owning 128 of the 256 columns.
+//
+// Epilogue. An in-kernel timeline (tools/gemm_trace.cu) showed the mainloop at ~6.3 us per tile
+// (about 1600 TFLOP/s) but an LDG/STG epilogue at 8-13 us per fp32 tile: two warps per scheduler,
+// ~650 dependent instructions per 32-column chunk (address arithmetic, bound checks, a transpose
+// through shared memory), plus ~1 us per tile in the cluster-scope release of the tmem_empty
+// arrive. Now: per 32-column chunk a lane (= one accumulator row) adds the fp32 residual it
+// fetched with four 256-bit loads one chunk earlier (whole sectors, so row-per-lane access is
+// not wasteful), writes the fp32 result and the 16-bit copy into TMA-swizzled staging boxes,
+// and one elected lane issues the two TMA stores. The warp computes no store address, rows
+// beyond M are clipped by the tensor maps, and the next TMEM chunk is always in flight.
 #pragma once
 
 #include "common.cuh"
@@ -25,19 +34,24 @@ namespace b200 {
 
 constexpr int kGemm2Threads = 384;
 constexpr int kGemm2BlockN = 256;
-constexpr int kGemm2Stages = 6;
+constexpr int kGemm2Stages = 5;
+constexpr int kGemm2ChunkCols = 32;  // accumulator columns per epilogue step
 
 struct Gemm2Smem {
     static constexpr int kABytes = 128 * 128;  // this CTA's 128 rows of A, one 128-byte swizzle span
     static constexpr int kBBytes = 128 * 128;  // this CTA's half (128 rows) of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // per epilogue warp: a 32-row x 32-word transpose buffer (row pitch 33 words: conflict-free
-    // for both the row-per-lane writes and the 4-rows-per-instruction coalesced read-back)
-    static constexpr int kStagePitch = 33;
-    static constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;
-    static constexpr int kStagingOffset = kGemm2Stages * kStageBytes;
-    static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
-    static constexpr int kTotal = kBarOffset + (2 * kGemm2Stages + 4) * 8 + 16 + 1024;
+    // per epilogue warp: one 32-row x 32-column fp32 staging box (128-byte rows, SWIZZLE_128B)
+    // and two 16-bit boxes (64-byte rows, SWIZZLE_64B). A TMA store has read its box well within
+    // one chunk period (measured), so the fp32 box is not double-buffered.
+    static constexpr int kBox32Bytes = 32 * kGemm2ChunkCols * 4;
+    static constexpr int kBox16Bytes = 32 * kGemm2ChunkCols * 2;
+    static constexpr int kEpiWarpBytes = kBox32Bytes + 2 * kBox16Bytes;
+    static constexpr int kEpiOffset = kGemm2Stages * kStageBytes;
+    static constexpr int kBarOffset = kEpiOffset + 8 * kEpiWarpBytes;
+    // full[stages], empty[stages], tmem_full[2], tmem_empty[2]
+    static constexpr int kNumBars = 2 * kGemm2Stages + 4;
+    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
 };
 static_assert(Gemm2Smem::kTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
@@ -56,8 +70,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// The only data this arrive orders is TMEM traffic, which tcgen05.fence::before_thread_sync
+// already covers; a .release at cluster scope would add a MEMBAR.GPU that waits ~1 us for every
+// outstanding global access of the warp (tools/gemm_trace.cu).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                  : "memory");
 }
 // TMA load into THIS CTA's shared memory; completion bytes are signalled on `mbar_cluster_addr`
@@ -106,10 +123,14 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
                  : "memory");
 }
 
-template <typename InT, typename OutT>
+// tmap_o32: fp32 [M, n_store] output, box 32 x 32, SWIZZLE_128B (used when p.has32);
+// tmap_o16: 16-bit [M, n_store] output or operand copy, box 32 x 32, SWIZZLE_64B (p.has16).
+template <typename InT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                      const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_o32,
+                      const __grid_constant__ CUtensorMap tmap_o16, const GemmParams p) {
     using SM = Gemm2Smem;
     constexpr int BLOCK_N = kGemm2BlockN;
     constexpr int BLOCK_K = 64;
@@ -128,6 +149,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     pdl_launch_dependents();
+    if (threadIdx.x == 0) B200_TRACE(0);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -144,6 +166,10 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
+    if (warp == 3 && lane == 0) {
+        if (p.has32) tma_prefetch_desc(&tmap_o32);
+        if (p.has16) tma_prefetch_desc(&tmap_o16);
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);   // leader's: one arrive.expect_tx by the leader's producer
@@ -159,6 +185,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc05_fence_before();
     cluster_sync_all();  // peer barriers initialised, TMEM allocated in both CTAs
     tc05_fence_after();
+    if (threadIdx.x == 0) B200_TRACE(1);
     pdl_wait();  // barrier init, TMEM allocation and the cluster sync overlap the predecessor's tail
     const uint32_t tmem_base = *tmem_slot;
 
@@ -200,6 +227,8 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            int trace_tile = 0;
+            (void)trace_tile;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc05_fence_after();
@@ -207,6 +236,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc05_fence_after();
+                    if (kb == 0 && trace_tile < 4) B200_TRACE(2 + 2 * trace_tile);  // first operands landed
                     const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
                     const uint64_t a_desc = umma_desc_k_sw128(sa);
                     const uint64_t b_desc = umma_desc_k_sw128(sa + SM::kABytes);
@@ -221,6 +251,8 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
                 umma_commit_2cta(&tmem_full[acc]);  // accumulators of both CTAs complete
+                if (trace_tile < 4) B200_TRACE(3 + 2 * trace_tile);  // last MMA of the tile issued
+                ++trace_tile;
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -230,77 +262,105 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------ epilogue (both CTAs) ------------------------------
-        // Each warp drains 32 accumulator rows (its TMEM lane quarter) x 128 columns. TMEM hands
-        // every lane one ROW; global memory wants one instruction to cover whole 128-byte lines.
-        // So each chunk of 32 output words per row is transposed through a per-warp smem buffer:
-        // bias / activation are applied row-per-lane, then 8 lanes cover 128 contiguous bytes of
-        // one row for the residual load and the store (4 rows per instruction, 4 lines instead
-        // of 32).
-        const int q = warp & 3;          // TMEM lane quarter
-        const int hh = (warp - 4) >> 2;  // which 128-column half of the tile
-        constexpr bool kOut32 = sizeof(OutT) == 4;
-        constexpr int kColsPerChunk = kOut32 ? 32 : 64;  // 32 words of output per row either way
-        constexpr int kChunks = 128 / kColsPerChunk;
-        constexpr int kPitch = SM::kStagePitch;
-        uint32_t* stg = reinterpret_cast<uint32_t*>(smem + SM::kStagingOffset) + (warp - 4) * 32 * kPitch;
-        const int sub_row = lane >> 3;       // coalesced phase: row within a group of 4
-        const int sub_w = (lane & 7) * 4;    // coalesced phase: first of 4 words
+        // Each warp drains 32 accumulator rows (its TMEM lane quarter) x 128 columns in four
+        // 32-column steps; a lane owns one row. Staging boxes use the TMA swizzles, so the
+        // row-per-lane 128-bit writes are bank-conflict-free: the 16-byte group j of row r sits
+        // at slot j ^ (r & 7) of its 128-byte fp32 row and at slot j ^ ((r >> 1) & 3) of its
+        // 64-byte 16-bit row.
+        constexpr int CH = kGemm2ChunkCols;
+        constexpr int kChunks = 128 / CH;
+        const int ew = warp - 4;
+        const int q = warp & 3;   // TMEM lane quarter
+        const int hh = ew >> 2;   // which 128-column half of the tile
+        const uint32_t box32 = smem_u32(smem + SM::kEpiOffset + ew * SM::kEpiWarpBytes);
+        const uint32_t ring16 = box32 + SM::kBox32Bytes;
+        const uint32_t row32 = box32 + lane * 128, swz32 = lane & 7;
+        const uint32_t row16 = lane * 64, swz16 = (lane >> 1) & 3;
+        const bool has32 = p.has32 != 0;
+        const bool has16 = p.has16 != 0;
+        const bool has_res = has32 && p.residual != nullptr;
+        int slot16 = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        OutT* out = reinterpret_cast<OutT*>(p.out);
         const uint32_t tmem_empty_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
         const uint32_t tmem_empty_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
+        int trace_tile = 0;
+        (void)trace_tile;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int n_blk = tile % num_n;
             const int m_blk = tile / num_n;
             const int row_base = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
-            const int row = row_base + lane;  // row-per-lane phase
-            const bool row_zero = row < p.M && p.row_valid != nullptr && p.row_valid[row] == 0;
+            const int row = row_base + lane;
+            const bool row_ok = row < p.M;
+            const bool row_zero = row_ok && p.row_valid != nullptr && p.row_valid[row] == 0;
+            const bool any_zero = __any_sync(0xffffffffu, row_zero);  // halo rows are rare
             const int ncol0 = n_blk * BLOCK_N + hh * 128;
-            const bool has_res = kOut32 && p.residual != nullptr;
-            float4 res[2][8];
-            auto load_res = [&](int c, float4 (&dst)[8]) {
+            // this lane's residual row: 128 contiguous bytes per chunk, fetched as whole sectors
+            const float* res_row = has_res && row_ok
+                                       ? p.residual + static_cast<size_t>(row) * p.ld_res + ncol0
+                                       : nullptr;
+            float res[2][CH];  // two chunks of lookahead
+            auto load_res = [&](int c, float (&dst)[CH]) {
+                if (res_row != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int grow = row_base + i * 4 + sub_row;
-                    if (grow < p.M)
-                        dst[i] = *reinterpret_cast<const float4*>(
-                            p.residual + static_cast<size_t>(grow) * p.ld_res + ncol0 + c * 32 + sub_w);
+                    for (int j = 0; j < CH / 8; ++j) ldg_256(res_row + c * CH + j * 8, &dst[j * 8]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) dst[j] = 0.f;
                 }
             };
-            if (has_res) load_res(0, res[0]);  // in flight while the mainloop finishes
+            if (has_res) {  // in flight while the mainloop finishes
+                load_res(0, res[0]);
+                load_res(1, res[1]);
+            }
             // fused RMSNorm, consumer side: per-row 1/rms from the producer's eight partial sums
             float rscale = 1.f;
-            if (p.ss_in != nullptr && row < p.M) {
+            if (p.ss_in != nullptr && row_ok) {
                 const float4* sp = reinterpret_cast<const float4*>(p.ss_in + static_cast<size_t>(row) * 8);
                 const float4 s0 = sp[0], s1 = sp[1];
                 const float tot = ((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w));
                 rscale = rsqrtf(tot * p.ss_inv_dim + p.ss_eps);
             }
-            float ssq[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ssq[i] = 0.f;
+            float ssq = 0.f;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc05_fence_after();
+            if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(10 + 2 * trace_tile);  // accumulator ready
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                     static_cast<uint32_t>(acc * BLOCK_N + hh * 128);
+            uint32_t r_next[CH];
+            tmem_ld_32x32(t_base, r_next);  // chunk c+1 is in flight while chunk c is processed
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
-                const int cur = c & 1, nxt = cur ^ 1;
-                const int n0 = ncol0 + c * kColsPerChunk;
-                uint32_t r[kColsPerChunk];
-                tmem_ld_32x32(t_base + c * kColsPerChunk, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                if constexpr (!kOut32)
-                    tmem_ld_32x32(t_base + c * kColsPerChunk + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-                if (c + 1 < kChunks && has_res) load_res(c + 1, res[nxt]);
+                const int n0 = ncol0 + c * CH;
+#ifdef B200_GEMM_TRACE
+                const bool tr = warp == 4 && lane == 0 && trace_tile < 2;
+                const int tslot = 32 + trace_tile * 48 + c * 6;
+                if (tr) B200_TRACE(tslot + 0);
+#endif
+                const uint32_t buf16 = ring16 + slot16 * SM::kBox16Bytes;
                 tmem_ld_wait();
-                float v[kColsPerChunk];
+                float v[CH];
 #pragma unroll
-                for (int j = 0; j < kColsPerChunk; ++j) v[j] = __uint_as_float(r[j]) * rscale;
+                for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r_next[j]);
+                if (c + 1 < kChunks) {
+                    tmem_ld_32x32(t_base + (c + 1) * CH, r_next);
+                } else {
+                    // the accumulator stage is drained: hand it back before finishing the chunk
+                    tc05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
+                }
+#ifdef B200_GEMM_TRACE
+                if (tr) B200_TRACE(tslot + 2);  // accumulator chunk in registers
+#endif
+                if (p.ss_in != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) v[j] *= rscale;
+                }
                 if (p.bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-                    for (int j = 0; j < kColsPerChunk / 4; ++j) {
+                    for (int j = 0; j < CH / 4; ++j) {
                         const float4 b = __ldg(b4 + j);
                         v[4 * j + 0] += b.x;
                         v[4 * j + 1] += b.y;
@@ -310,94 +370,87 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 if (p.act == kActSilu) {
 #pragma unroll
-                    for (int j = 0; j < kColsPerChunk; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+                    for (int j = 0; j < CH; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
                 }
-                if (row_zero) {
+                if (has_res) {
 #pragma unroll
-                    for (int j = 0; j < kColsPerChunk; ++j) v[j] = 0.f;
+                    for (int j = 0; j < CH; ++j) v[j] += res[c & 1][j];
+                    if (c + 2 < kChunks) load_res(c + 2, res[c & 1]);
                 }
-                // row-per-lane -> smem (lane stride 33 words: conflict-free)
+                if (any_zero) {  // halo rows stay zero, with or without a residual
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if constexpr (kOut32) stg[lane * kPitch + j] = __float_as_uint(v[j]);
-                    else stg[lane * kPitch + j] = Half16<OutT>::pack(v[2 * j], v[2 * j + 1]);
+                    for (int j = 0; j < CH; ++j) v[j] = row_zero ? 0.f : v[j];
                 }
+                // the boxes this chunk writes were last read by the stores of chunk g-1 (fp32)
+                // and g-2 (16-bit); those are normally long done
+                if (lane == 0) bulk_wait_group_read<0>();
                 __syncwarp();
-                // smem -> global, 8 lanes per 128-byte row segment
+#ifdef B200_GEMM_TRACE
+                if (tr) B200_TRACE(tslot + 1);  // staging boxes free
+#endif
+                if (has32) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = i * 4 + sub_row;
-                    const int grow = row_base + rr;
-                    uint4 w;
-                    w.x = stg[rr * kPitch + sub_w + 0];
-                    w.y = stg[rr * kPitch + sub_w + 1];
-                    w.z = stg[rr * kPitch + sub_w + 2];
-                    w.w = stg[rr * kPitch + sub_w + 3];
-                    if (grow < p.M) {
-                        if constexpr (kOut32) {
-                            float4 o = make_float4(__uint_as_float(w.x), __uint_as_float(w.y),
-                                                   __uint_as_float(w.z), __uint_as_float(w.w));
-                            if (has_res) {
-                                o.x += res[cur][i].x;
-                                o.y += res[cur][i].y;
-                                o.z += res[cur][i].z;
-                                o.w += res[cur][i].w;
-                                // halo rows stay zero even when a residual is added
-                                if (p.row_valid != nullptr && p.row_valid[grow] == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                            *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldc + n0 + sub_w) = o;
-                            // fused RMSNorm, producer side: 16-bit copy + row sum of squares
-                            if (p.out16 != nullptr) {
-                                uint2 h2;
-                                h2.x = Half16<InT>::pack(o.x, o.y);
-                                h2.y = Half16<InT>::pack(o.z, o.w);
-                                *reinterpret_cast<uint2*>(reinterpret_cast<InT*>(p.out16) +
-                                                          static_cast<size_t>(grow) * p.ld16 + n0 + sub_w) = h2;
-                            }
-                            ssq[i] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq[i]))));
-                        } else {
-                            *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldc + n0 + 2 * sub_w) = w;
-                        }
+                    for (int j = 0; j < CH / 4; ++j)
+                        sts_128(row32 + ((static_cast<uint32_t>(j) ^ swz32) << 4),
+                                __float_as_uint(v[4 * j + 0]), __float_as_uint(v[4 * j + 1]),
+                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    // fused RMSNorm, producer side: row sum of squares (fixed order)
+                    if (p.ss_out != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) ssq = fmaf(v[j], v[j], ssq);
                     }
                 }
-                __syncwarp();  // staging buffer is reused by the next chunk
-            }
-            tc05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
-            if constexpr (kOut32) {
-                if (p.ss_out != nullptr) {
-                    // 8 lanes hold the 128 columns of one row: fixed-order butterfly, one slot per warp
+                if (has16) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float t = ssq[i];
-                        t += __shfl_xor_sync(0xffffffffu, t, 1);
-                        t += __shfl_xor_sync(0xffffffffu, t, 2);
-                        t += __shfl_xor_sync(0xffffffffu, t, 4);
-                        const int grow = row_base + i * 4 + sub_row;
-                        if ((lane & 7) == 0 && grow < p.M)
-                            p.ss_out[static_cast<size_t>(grow) * 8 + (ncol0 >> 7)] = t;
-                    }
+                    for (int j = 0; j < CH / 8; ++j)
+                        sts_128(buf16 + row16 + ((static_cast<uint32_t>(j) ^ swz16) << 4),
+                                Half16<InT>::pack(v[8 * j + 0], v[8 * j + 1]),
+                                Half16<InT>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                Half16<InT>::pack(v[8 * j + 4], v[8 * j + 5]),
+                                Half16<InT>::pack(v[8 * j + 6], v[8 * j + 7]));
                 }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+#ifdef B200_GEMM_TRACE
+                if (tr) B200_TRACE(tslot + 3);  // staged + fenced
+#endif
+                if (lane == 0) {
+                    if (has32) tma_store_2d(&tmap_o32, box32, n0, row_base);
+                    if (has16) tma_store_2d(&tmap_o16, buf16, n0, row_base);
+                    bulk_commit_group();
+#ifdef B200_GEMM_TRACE
+                    if (tr) B200_TRACE(tslot + 4);  // stores issued
+#endif
+                }
+                slot16 ^= 1;
             }
+            if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(11 + 2 * trace_tile);  // tile drained
+            ++trace_tile;
+            if (has32 && p.ss_out != nullptr && row_ok)
+                p.ss_out[static_cast<size_t>(row) * 8 + (ncol0 >> 7)] = ssq;  // one slot per 128 columns
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        // the staging boxes must outlive their readers; completion of the writes themselves is
+        // ordered by the end of the grid
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
     }
 
     // the leader's MMAs read the peer's shared memory: neither CTA may exit early
     tc05_fence_before();
     cluster_sync_all();
     tc05_fence_after();
+    if (threadIdx.x == 0) B200_TRACE(20);
     if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
-template <typename InT, typename OutT>
-int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                          cudaStream_t stream) {
-    auto kern = gemm_tc05_2cta_kernel<InT, OutT>;
+template <typename InT>
+int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to32,
+                          const CUtensorMap& to16, const GemmParams& p, cudaStream_t stream) {
+    auto kern = gemm_tc05_2cta_kernel<InT>;
     static PerDeviceOnce once;
     if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -408,7 +461,8 @@ int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     int clusters = num_m * num_n;
     if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
     if (clusters < 1) return 0;
-    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2Smem::kTotal, stream, ta, tb, p));
+    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2Smem::kTotal, stream, ta, tb,
+                               to32, to16, p));
     return 0;
 }
 
