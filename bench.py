@@ -360,7 +360,7 @@ def run_ours(args):
         peak = peaks["tflops_sustained"]
         step_flops = (LINEAR_FLOPS_PER_TOKEN + ATTN_FLOPS_PER_TOKEN_PER_T * tokens) * total_tokens
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01b_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")
         if os.path.exists(tpath) and args.workload == "c2":
             with open(tpath) as f:
                 traffic = json.load(f)["mean_dram_bytes_per_launch"]  # bytes per launch, from the ncu capture
