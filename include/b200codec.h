@@ -156,6 +156,16 @@ int b200codec_stage_times(B200Codec* h, int max_stages, const char** names_out,
 int b200codec_fsq_lookup(B200Codec* h, const void* ids_dev, int id_type, int64_t n,
                          float* out_dev, void* stream);
 
+/* Encode-direction FSQ: ResidualFSQ.forward as called by Encoder.quantize
+ * (tts/core/codec/encoder.py:73-78; vector-quantize-pytorch 1.17.8, one quantizer, levels [4]*8):
+ * feats_dev [n_tokens, ld] fp32 token-major (ld >= 2048) -> ids (id_type 0: int32, 1: int64):
+ * z = project_in(x); digit_d = rint(tanh(z_d + shift) * half_l - 0.5) + 2; id = sum_d digit_d * 4^d.
+ * z_dev (optional, [n_tokens, 8]) receives the projected values. pre_bound != 0 applies FSQ.bound
+ * once more before the layer (library releases differ; see oracle/codec_oracle.py::fsq_quantize).
+ * Asynchronous on `stream`. */
+int b200codec_fsq_quantize(B200Codec* h, const float* feats_dev, int ld, int64_t n_tokens,
+                           void* ids_dev, int id_type, float* z_dev, int pre_bound, void* stream);
+
 /* K13+K14, ISTFTHead.forward after the Linear + ISTFT.forward "same"
  * (tts/core/codec/decoder_modules.py:131-148, 35-93): x_pred_dev is the head Linear output,
  * packed [sum(T), ld] fp32 (cols 0..640 log-magnitude, 641..1281 phase); writes

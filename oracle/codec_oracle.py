@@ -34,6 +34,35 @@ def fsq_codes(ids: torch.Tensor) -> torch.Tensor:
     return (digits.to(torch.float32) - half_width) / half_width
 
 
+def fsq_bound(z: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
+    """FSQ.bound (vector-quantize-pytorch 1.17.8, finite_scalar_quantization.py) for levels [4]*8:
+    half_l = (levels - 1) * (1 + eps) / 2; offset = 0.5 (even levels); shift = atanh(offset / half_l);
+    tanh(z + shift) * half_l - offset."""
+    levels = torch.full((8,), 4, dtype=torch.int32)
+    half_l = (levels - 1) * (1 + eps) / 2
+    offset = torch.where(levels % 2 == 0, 0.5, 0.0)
+    shift = (offset / half_l).atanh()
+    return (z + shift).tanh() * half_l - offset
+
+
+def fsq_quantize(sd: SD, feats: torch.Tensor, pre_bound: bool = False):
+    """ResidualFSQ.forward as called by Encoder.quantize (tts/core/codec/encoder.py:73-78), one
+    quantizer: feats (..., 2048) -> (ids int64 (...,), z (..., 8), bounded (..., 8)).
+        z = project_in(x); codes = round(bound(z)) / half_width;
+        ids = sum((codes * half_width + half_width) * basis), basis = cumprod([1, 4, ...]) (int32)
+    `pre_bound`: some releases run `residual = layers[0].bound(x)` before the layer loop (the
+    wheel is absent here, so which one 1.17.8 does is unpinned); the flag selects that variant.
+    "parity unpinned": restated from the library's published source, not executed upstream code."""
+    z = F.linear(feats, sd["decoder.quantizer.project_in.weight"], sd["decoder.quantizer.project_in.bias"])
+    r = fsq_bound(z) if pre_bound else z
+    bounded = fsq_bound(r)
+    half_width = 2
+    codes = bounded.round() / half_width                      # round_ste forward value
+    basis = torch.cumprod(torch.tensor([1] + [4] * 7), dim=0).to(torch.int32)
+    ids = ((codes * half_width + half_width) * basis).sum(dim=-1).to(torch.int32)
+    return ids.to(torch.int64), z, bounded
+
+
 def fsq_lookup(sd: SD, ids: torch.Tensor) -> torch.Tensor:
     """ids (B, T) -> (B, T, 2048): project_out(codes) (scales == 1 for the single quantizer)."""
     codes = fsq_codes(ids)

@@ -2,8 +2,9 @@
 
 The wheel is not installed here and not vendored in /root/reference. This restates, from the
 library's published source, exactly the part of `ResidualFSQ` the reference decoder touches
-(construction at decoder_modules.py:418-420, `get_output_from_indices` at decoder.py:77), so the
-UNMODIFIED reference modules can be imported by oracle/make_golden.py. "parity unpinned": this
+(construction at decoder_modules.py:418-420, `get_output_from_indices` at decoder.py:77) and the
+reference encoder's quantise step (`forward`, called at encoder.py:76), so the UNMODIFIED
+reference modules can be imported by oracle/make_golden*.py. "parity unpinned": this
 file is a restatement, not the upstream code.
 """
 
@@ -44,3 +45,22 @@ class ResidualFSQ(torch.nn.Module):
     def get_output_from_indices(self, indices):
         codes = self.get_codes_from_indices(indices)
         return self.project_out(codes.sum(dim=0))
+
+    # ---- encode direction (Encoder.quantize, encoder.py:73-78) ----
+    pre_bound = False  # class switch: `residual = layers[0].bound(x)` before the layer loop
+
+    def _bound(self, z, eps=1e-3):
+        half_l = (self._levels - 1) * (1 + eps) / 2
+        offset = torch.where(self._levels % 2 == 0, 0.5, 0.0)
+        shift = (offset / half_l).atanh()
+        return (z + shift).tanh() * half_l - offset
+
+    def forward(self, x):
+        """x [b, n, dim] -> (quantized_out [b, n, dim], indices [b, n, 1] int32)."""
+        z = self.project_in(x)
+        residual = self._bound(z) if self.pre_bound else z
+        half_width = self._levels // 2
+        codes = self._bound(residual / self.scales).round() / half_width       # FSQ.quantize
+        indices = ((codes * half_width + half_width) * self._basis).sum(dim=-1).to(torch.int32)
+        quantized_out = self.project_out(codes * self.scales)
+        return quantized_out, indices.unsqueeze(-1)

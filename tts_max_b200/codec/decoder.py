@@ -394,6 +394,32 @@ class Decoder(torch.nn.Module):
             return False
         return bool(_lib.load().b200codec_take_id_error(self._handle))
 
+    @torch.no_grad()
+    def quantize_features(self, feats: torch.Tensor, pre_bound: bool = False,
+                          return_projection: bool = False):
+        """Encode-direction FSQ with this checkpoint's `quantizer.project_in`: token-major
+        features (n_tokens, 2048) fp32 on the device -> int64 ids (n_tokens,)
+        [+ the (n_tokens, 8) projected values]. See `codec.encoder.FSQQuantizer`."""
+        handle = self._ensure_handle()
+        lib = _lib.load()
+        if feats.device != self._device or feats.dim() != 2 or feats.dtype != torch.float32:
+            raise ValueError("features must be a 2-D float32 tensor on the decoder's device")
+        if feats.stride(1) != 1 or feats.stride(0) % 4 != 0 or feats.data_ptr() % 16 != 0:
+            feats = feats.contiguous()
+        n = feats.shape[0]
+        with torch.cuda.device(self._device):
+            ids = torch.empty(n, dtype=torch.int64, device=self._device)
+            z = torch.empty(n, 8, dtype=torch.float32, device=self._device) if return_projection else None
+            if n == 0:
+                return (ids, z) if return_projection else ids
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(lib.b200codec_fsq_quantize(
+                handle, ctypes.c_void_p(feats.data_ptr()), int(feats.stride(0)) if n > 1 else feats.shape[1], n,
+                ctypes.c_void_p(ids.data_ptr()), _lib.IDS_I64,
+                ctypes.c_void_p(z.data_ptr()) if z is not None else None, 1 if pre_bound else 0,
+                ctypes.c_void_p(stream)))
+        return (ids, z) if return_projection else ids
+
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_lib.load().b200codec_launch_count(self._handle))
 

@@ -1325,6 +1325,22 @@ int b200codec_fsq_lookup(B200Codec* h, const void* ids_dev, int id_type, int64_t
     return 0;
 }
 
+int b200codec_fsq_quantize(B200Codec* h, const float* feats_dev, int ld, int64_t n_tokens, void* ids_dev,
+                           int id_type, float* z_dev, int pre_bound, void* stream) {
+    B200_CHECK(h && feats_dev && ids_dev, "fsq_quantize: null argument");
+    B200_CHECK(id_type == 0 || id_type == 1, "fsq_quantize: id_type must be 0 (int32) or 1 (int64)");
+    B200_CHECK(n_tokens >= 0 && n_tokens <= 0x7fffffff, "fsq_quantize: bad token count");
+    const float* w = h->m("decoder.quantizer.project_in.weight");
+    const float* b = h->m("decoder.quantizer.project_in.bias");
+    B200_CHECK(w && b, "fsq_quantize: quantizer.project_in has not been loaded");
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    if (launch_fsq_quantize(feats_dev, ld, static_cast<int>(n_tokens), w, b, h->V, pre_bound, ids_dev, id_type,
+                            z_dev, static_cast<cudaStream_t>(stream)))
+        return 1;
+    h->launches++;
+    return 0;
+}
+
 int b200codec_istft(B200Codec* h, const float* x_pred_dev, int ld, const int32_t* seqlens_host,
                     int n_utts, float* wav_dev, void* stream) {
     B200_CHECK(h && x_pred_dev && wav_dev && seqlens_host, "istft: null argument");

@@ -124,6 +124,84 @@ fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_t
     }
 }
 
+// ---------------------------------------------------------------------------
+// FSQ quantise (encode direction): the mirror image of the lookup above.
+//
+// Replaces vector_quantize_pytorch.ResidualFSQ.forward as called by Encoder.quantize
+// (tts/core/codec/encoder.py:73-78; one quantizer, levels [4]*8, dim 2048):
+//   z      = project_in(x)                       Linear 2048 -> 8 (+ bias)
+//   b      = tanh(z + shift) * half_l - offset   FSQ.bound: half_l = 3 * 1.001 / 2, offset = 0.5,
+//                                                shift = atanh(offset / half_l)
+//   digit  = rint(b) + 2  in {0, 1, 2, 3}        round_ste; half_width = 2
+//   id     = sum_d digit_d * 4^d                 codes_to_indices, basis = cumprod([1, 4, ...])
+// `pre_bound`: releases of the library differ in whether ResidualFSQ bounds the projected input
+// once more before its first layer (residual = layers[0].bound(x)); 1 applies it.
+//
+// HBM-bound: 8 KB of fp32 features in, one id out per token. A warp reduces four tokens at a
+// time against the 64 KB projection (L1-resident); the summation order is fixed (lane-serial
+// over 16 float4 slabs, then an xor butterfly), so a token's id does not depend on the batch.
+constexpr int kFsqQTokensPerWarp = 4;
+
+__device__ __forceinline__ float fsq_bound(float z, float half_l, float shift) {
+    return tanhf(z + shift) * half_l - 0.5f;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kFsqThreads)
+fsq_quantize_kernel(const float* __restrict__ x, int ld, int n_tokens, const float* __restrict__ w_in,
+                    const float* __restrict__ b_in, int dim, float half_l, float shift, int pre_bound,
+                    IdT* __restrict__ ids, float* __restrict__ z_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * kFsqThreads + threadIdx.x) >> 5;
+    const int tok0 = warp_global * kFsqQTokensPerWarp;
+    if (tok0 >= n_tokens) return;
+    float acc[kFsqQTokensPerWarp][8];
+#pragma unroll
+    for (int t = 0; t < kFsqQTokensPerWarp; ++t)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[t][d] = 0.f;
+    for (int c = lane * 4; c < dim; c += 128) {
+        float4 w[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) w[d] = __ldg(reinterpret_cast<const float4*>(w_in + static_cast<size_t>(d) * dim + c));
+#pragma unroll
+        for (int t = 0; t < kFsqQTokensPerWarp; ++t) {
+            const int tok = min(tok0 + t, n_tokens - 1);
+            const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * ld + c);
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                acc[t][d] = fmaf(v.w, w[d].w, fmaf(v.z, w[d].z, fmaf(v.y, w[d].y, fmaf(v.x, w[d].x, acc[t][d]))));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kFsqQTokensPerWarp; ++t)
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[t][d] += __shfl_xor_sync(0xffffffffu, acc[t][d], o);
+    // lane l finishes (token l / 8, dimension l % 8)
+    const int t_sel = lane >> 3, d_sel = lane & 7;
+    float z = 0.f;
+#pragma unroll
+    for (int t = 0; t < kFsqQTokensPerWarp; ++t)
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (t == t_sel && d == d_sel) z = acc[t][d];
+    z += __ldg(b_in + d_sel);
+    const int tok = tok0 + t_sel;
+    if (z_out != nullptr && tok < n_tokens) z_out[static_cast<size_t>(tok) * 8 + d_sel] = z;
+    float b = z;
+    if (pre_bound) b = fsq_bound(b, half_l, shift);
+    b = fsq_bound(b, half_l, shift);
+    int digit = static_cast<int>(rintf(b)) + 2;  // torch.round: half to even
+    digit = min(max(digit, 0), 3);
+    unsigned id = static_cast<unsigned>(digit) << (2 * d_sel);
+    id |= __shfl_xor_sync(0xffffffffu, id, 1);
+    id |= __shfl_xor_sync(0xffffffffu, id, 2);
+    id |= __shfl_xor_sync(0xffffffffu, id, 4);
+    if (d_sel == 0 && tok < n_tokens) ids[tok] = static_cast<IdT>(id);
+}
+
 template <typename OutT>
 int launch_typed(const void* ids, int id_type, const int32_t* row_tok, int rows,
                  const float* w_out, const float* b_out, int channels, void* out, int ld,
@@ -162,6 +240,26 @@ int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int 
                                     err_flag, stream);
     set_error("fsq: unsupported output precision %d", out_prec);
     return 1;
+}
+
+int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in, const float* b_in,
+                        int dim, int pre_bound, void* ids, int id_type, float* z_out, cudaStream_t stream) {
+    if (n_tokens <= 0) return 0;
+    B200_CHECK(dim % 128 == 0 && ld >= dim && ld % 4 == 0, "fsq_quantize: bad dim %d / ld %d", dim, ld);
+    B200_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fsq_quantize: features must be 16-byte aligned");
+    // the constants of FSQ.bound for levels = 4, evaluated in fp32 as the library does
+    const float half_l = 3.0f * 1.001f / 2.0f;
+    const float shift = atanhf(0.5f / half_l);
+    const int tokens_per_block = (kFsqThreads / 32) * kFsqQTokensPerWarp;
+    const int grid = (n_tokens + tokens_per_block - 1) / tokens_per_block;
+    if (id_type == 1)
+        fsq_quantize_kernel<long long><<<grid, kFsqThreads, 0, stream>>>(
+            x, ld, n_tokens, w_in, b_in, dim, half_l, shift, pre_bound, static_cast<long long*>(ids), z_out);
+    else
+        fsq_quantize_kernel<int><<<grid, kFsqThreads, 0, stream>>>(x, ld, n_tokens, w_in, b_in, dim, half_l, shift,
+                                                                  pre_bound, static_cast<int*>(ids), z_out);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace b200

@@ -166,33 +166,64 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
     for (int i = threadIdx.x; i < kIstftOutHops * kHop; i += kIstftThreads) sm.ola[i] = 0.f;
     __syncthreads();
 
+    // The head output of a frame group is fetched into registers one group ahead (kGroup * kKi
+    // (log-magnitude, phase) pairs per thread), so the HBM/L2 latency hides behind the FFT passes
+    // of the previous group instead of stalling the spectrum phase.
+    constexpr int kKi = (kBins + kIstftThreads - 1) / kIstftThreads;
+    float lm[kGroup][kKi], ph[kGroup][kKi];
+    auto fetch_group = [&](int g) {
+        const int t_first = b0 - 2 + g * kGroup;
+#pragma unroll
+        for (int f = 0; f < kGroup; ++f) {
+            const int t = t_first + f;
+            const bool t_ok = g < kTileFrames / kGroup && t >= 0 && t < T;
+            const float* row = x_pred + static_cast<size_t>(row0 + (t_ok ? t : 0)) * ld;
+#pragma unroll
+            for (int i = 0; i < kKi; ++i) {
+                const int k = threadIdx.x + i * kIstftThreads;
+                const bool ok = t_ok && k < kBins;
+                lm[f][i] = ok ? row[k] : 0.f;
+                ph[f][i] = ok ? row[kBins + k] : 0.f;
+            }
+        }
+    };
+    fetch_group(0);
+
     for (int g = 0; g < kTileFrames / kGroup; ++g) {
         const int t_first = b0 - 2 + g * kGroup;  // absolute frame index of group slot 0
-        if (t_first >= T || t_first + kGroup <= 0) continue;  // uniform: whole group outside
+        if (t_first >= T || t_first + kGroup <= 0) {  // uniform: whole group outside
+            fetch_group(g + 1);
+            continue;
+        }
 
         // 1. spectrum: X[k] = min(exp(m_k), 100) * (cos p_k, sin p_k); Re X[640] parked in X[0].y
-        for (int idx = threadIdx.x; idx < kGroup * kBins; idx += kIstftThreads) {
-            const int f = idx / kBins;
-            const int k = idx - f * kBins;
+#pragma unroll
+        for (int f = 0; f < kGroup; ++f) {
             const int t = t_first + f;
-            float2 X = make_float2(0.f, 0.f);
-            if (t >= 0 && t < T) {
-                const float* row = x_pred + static_cast<size_t>(row0 + t) * ld;
-                // exp via MUFU.EX2, sin/cos via MUFU after a two-term Cody-Waite reduction to
-                // [-pi, pi] (abs error ~5e-7, three orders below the GEMM operand rounding)
-                const float mag = fminf(__expf(row[k]), 100.f);
-                const float ph = row[kBins + k];
-                const float kq = rintf(ph * 0.15915494309189535f);
-                float rr = fmaf(kq, -6.2831854820251465f, ph);   // 2*pi (fp32 high part)
-                rr = fmaf(kq, 1.7484556000744487e-07f, rr);      // 2*pi low part: 2*pi = hi - 1.748e-7
-                float sn, cs;
-                __sincosf(rr, &sn, &cs);
-                X = make_float2(mag * cs, mag * sn);
+            const bool t_ok = t >= 0 && t < T;
+#pragma unroll
+            for (int i = 0; i < kKi; ++i) {
+                const int k = threadIdx.x + i * kIstftThreads;
+                if (k >= kBins) continue;
+                float2 X = make_float2(0.f, 0.f);
+                if (t_ok) {
+                    // exp via MUFU.EX2, sin/cos via MUFU after a two-term Cody-Waite reduction to
+                    // [-pi, pi] (abs error ~5e-7, three orders below the GEMM operand rounding)
+                    const float mag = fminf(__expf(lm[f][i]), 100.f);
+                    const float p0 = ph[f][i];
+                    const float kq = rintf(p0 * 0.15915494309189535f);
+                    float rr = fmaf(kq, -6.2831854820251465f, p0);   // 2*pi (fp32 high part)
+                    rr = fmaf(kq, 1.7484556000744487e-07f, rr);      // 2*pi low part: 2*pi = hi - 1.748e-7
+                    float sn, cs;
+                    __sincosf(rr, &sn, &cs);
+                    X = make_float2(mag * cs, mag * sn);
+                }
+                if (k == 0) sm.buf_b[f][0].x = X.x;            // Im X[0] ignored by irfft
+                else if (k == kHalf) sm.buf_b[f][0].y = X.x;   // Im X[640] ignored by irfft
+                else sm.buf_b[f][k] = X;
             }
-            if (k == 0) sm.buf_b[f][0].x = X.x;            // Im X[0] ignored by irfft
-            else if (k == kHalf) sm.buf_b[f][0].y = X.x;   // Im X[640] ignored by irfft
-            else sm.buf_b[f][k] = X;
         }
+        fetch_group(g + 1);  // lands during the pack / FFT / overlap-add phases below
         __syncthreads();
 
         // 2. pack: Z[k] = (X[k] + conj X[640-k]) + i * (X[k] - conj X[640-k]) * exp(+2 pi i k / 1280)

@@ -44,6 +44,10 @@ constexpr int kIstftOutHops = 12;   // output hops per ISTFT CTA (+4 halo frames
 int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int rows,
                       const float* w_out /*[C,8]*/, const float* b_out /*[C]*/, int channels,
                       void* out, int ld, int out_prec, int* err_flag, cudaStream_t stream);
+// encode direction (encoder.py:73-78): features [n_tokens, ld] fp32 -> ids (id_type 0: int32, 1: int64);
+// z_out (optional) receives the eight projected values per token
+int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in, const float* b_in,
+                        int dim, int pre_bound, void* ids, int id_type, float* z_out, cudaStream_t stream);
 
 // ---- norms.cu ----
 // w == nullptr: no elementwise weight (it is folded into the consumer GEMM's weight columns)
