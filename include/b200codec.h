@@ -131,6 +131,10 @@ int b200codec_take_id_error(B200Codec* h);
  * flash kernel it replaced (kept for A/B measurements and as a second opinion in the tests). */
 int b200codec_set_attention_impl(int impl);
 
+/* decode_host with a PINNED output buffer lets the last kernel store the PCM straight into host
+ * memory (default on; pageable buffers always take the staged device buffer + copy). A/B switch. */
+int b200codec_set_zero_copy_output(int on);
+
 /* Process-wide: launch the kernel chain with programmatic dependent launch (1, default) or as
  * plain stream-ordered launches (0; for A/B measurements). */
 int b200codec_set_pdl(int on);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200codec_decode_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_take_id_error": (c_int, [c_void_p]),
     "b200codec_set_attention_impl": (c_int, [c_int]),
+    "b200codec_set_zero_copy_output": (c_int, [c_int]),
     "b200codec_set_pdl": (c_int, [c_int]),
     "b200codec_samples_per_token": (c_int, [c_void_p]),
     "b200codec_launch_count": (c_int64, [c_void_p]),

@@ -25,6 +25,7 @@
 namespace b200 {
 
 int g_use_pdl = 1;
+static int g_zero_copy_out = 1;  // decode_host: write PCM directly into pinned host memory
 
 static thread_local char g_err[1024] = {0};
 
@@ -1263,11 +1264,26 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
     const size_t id_bytes = static_cast<size_t>(toks) * (id_type == B200CODEC_IDS_I64 ? 8 : 4);
     const size_t wav_bytes = static_cast<size_t>(toks) * h->hop * h->total_up * sizeof(float);
     if (h->io_ids.ensure(id_bytes)) return 1;
-    if (h->io_wav.ensure(wav_bytes)) return 1;
     B200_CUDA_OK(cudaMemcpyAsync(h->io_ids.p, ids_host, id_bytes, cudaMemcpyHostToDevice, s));
-    if (b200codec_decode_varlen(h, h->io_ids.p, id_type, seqlens_host, n_utts, h->io_wav.as<float>(), s))
-        return 1;
-    B200_CUDA_OK(cudaMemcpyAsync(wav_host, h->io_wav.p, wav_bytes, cudaMemcpyDeviceToHost, s));
+    // Pinned (page-locked, device-mapped) output: the ISTFT kernel stores the PCM straight into host
+    // memory, so the transfer overlaps the kernel instead of following it as a separate copy.
+    float* wav_mapped = nullptr;
+    if (g_zero_copy_out) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, wav_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr)
+            wav_mapped = static_cast<float*>(attr.devicePointer);
+        else
+            (void)cudaGetLastError();  // pageable memory: not an error, take the staged path
+    }
+    if (wav_mapped != nullptr) {
+        if (b200codec_decode_varlen(h, h->io_ids.p, id_type, seqlens_host, n_utts, wav_mapped, s)) return 1;
+    } else {
+        if (h->io_wav.ensure(wav_bytes)) return 1;
+        if (b200codec_decode_varlen(h, h->io_ids.p, id_type, seqlens_host, n_utts, h->io_wav.as<float>(), s))
+            return 1;
+        B200_CUDA_OK(cudaMemcpyAsync(wav_host, h->io_wav.p, wav_bytes, cudaMemcpyDeviceToHost, s));
+    }
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -1279,6 +1295,11 @@ int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0;
 int b200codec_set_attention_impl(int impl) {
     B200_CHECK(impl == 0 || impl == 1, "attention impl must be 0 (tcgen05) or 1 (mma.sync)");
     g_attention_impl = impl;
+    return 0;
+}
+
+int b200codec_set_zero_copy_output(int on) {
+    g_zero_copy_out = on != 0;
     return 0;
 }
 
