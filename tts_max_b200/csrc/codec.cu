@@ -136,6 +136,8 @@ struct B200Codec {
     UpStageW up[kMaxUp];
     void* w_out_proj = nullptr;
     float* head_bias_pad = nullptr;
+    float* w_pre = nullptr;  // fc_post_a o project_out folded: [C, 8] codebook projection ...
+    float* b_pre = nullptr;  // ... and [C] bias (fp32)
     float2* twiddle = nullptr;
     float *rope_cos = nullptr, *rope_sin = nullptr;
 
@@ -434,7 +436,7 @@ int ensure_workspace(B200Codec* h, int rows) {
     const size_t C = h->C;
     auto al = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
     const size_t Rlast = R * h->total_up;  // rows of the last (upsampled) row space
-    size_t sz_a0 = al(R * h->V * es), sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
+    size_t sz_a0 = 0 /* the 2048-wide FSQ output no longer exists: folded into fc_post_a */, sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
            sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(Rlast * h->head_ld * 4);
     size_t sz_ss = al(R * 8 * 4);
     size_t total = sz_a0 + 4 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho + sz_ss;
@@ -735,17 +737,14 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
     const RowSpace& rs = h->rs;
     B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * h->gn_slots * rs.n_utts * 64, s));
     {
+        // project_out (8 -> 2048, decoder.py:77) and fc_post_a (2048 -> 1024, decoder.py:79) are two
+        // linear maps back to back, so fc_post_a(project_out(code)) = W_pre code + b_pre with the
+        // [1024, 8] product folded in fp64 at load time: the same digit-unpack / 8-term lookup
+        // kernel as the stand-alone K1, one quarter of the bytes and no K = 2048 GEMM. Halo rows
+        // are written as zeros: this is the conv7 operand.
         Stage t(h, "fsq_lookup", s);
-        RUN(launch_fsq_lookup(ids_dev, id_type, rs.row_tok, rs.rows,
-                              h->m("decoder.quantizer.project_out.weight"),
-                              h->m("decoder.quantizer.project_out.bias"), h->V, h->a0, h->V, prec,
+        RUN(launch_fsq_lookup(ids_dev, id_type, rs.row_tok, rs.rows, h->w_pre, h->b_pre, C, h->xc, C, prec,
                               h->err_flag_dev, s));
-    }
-    {
-        Stage t(h, "fc_post_a_gemm", s);
-        // halo rows are written as zeros: this is the conv7 operand
-        RUN(gemm(h, h->a0, h->V, h->w_fc, C, 1, h->xc, false, C, C, h->m("fc_post_a.bias"),
-                 nullptr, kActNone, true, s));
     }
     {
         Stage t(h, "embed_conv7_gemm", s);
@@ -983,6 +982,8 @@ void b200codec_destroy(B200Codec* h) {
     if (h->plan_host) cudaFreeHost(h->plan_host);
     if (h->head_bias_pad) cudaFree(h->head_bias_pad);
     if (h->twiddle) cudaFree(h->twiddle);
+    if (h->w_pre) cudaFree(h->w_pre);
+    if (h->b_pre) cudaFree(h->b_pre);
     if (h->rope_cos) cudaFree(h->rope_cos);
     if (h->rope_sin) cudaFree(h->rope_sin);
     if (h->gn_stats) cudaFree(h->gn_stats);
@@ -1107,8 +1108,35 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     float* scratch = nullptr;
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&scratch), 3ull * C * C * sizeof(float)));
 
-    h->w_fc = take(static_cast<size_t>(C) * V);
+    h->w_fc = take(static_cast<size_t>(C) * V);  // 16-bit fc_post_a operand (b200codec_gemm parity tests)
     if (launch_repack_weight(prec, h->m("fc_post_a.weight"), h->w_fc, C, V, 1, s)) return 1;
+    {
+        // W_pre = W_fc W_out, b_pre = W_fc b_out + b_fc (fp64 on the host, stored fp32)
+        std::vector<float> wfc(static_cast<size_t>(C) * V), bfc(C), wo(static_cast<size_t>(V) * 8), bo(V);
+        B200_CUDA_OK(cudaMemcpy(wfc.data(), h->m("fc_post_a.weight"), wfc.size() * 4, cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(bfc.data(), h->m("fc_post_a.bias"), bfc.size() * 4, cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(wo.data(), h->m("decoder.quantizer.project_out.weight"), wo.size() * 4,
+                                cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(bo.data(), h->m("decoder.quantizer.project_out.bias"), bo.size() * 4,
+                                cudaMemcpyDeviceToHost));
+        std::vector<float> wp(static_cast<size_t>(C) * 8), bp(C);
+        for (int c = 0; c < C; ++c) {
+            double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double b = bfc[c];
+            const float* wr = &wfc[static_cast<size_t>(c) * V];
+            for (int v = 0; v < V; ++v) {
+                const double wv = wr[v];
+                for (int d = 0; d < 8; ++d) acc[d] += wv * wo[static_cast<size_t>(v) * 8 + d];
+                b += wv * bo[v];
+            }
+            for (int d = 0; d < 8; ++d) wp[static_cast<size_t>(c) * 8 + d] = static_cast<float>(acc[d]);
+            bp[c] = static_cast<float>(b);
+        }
+        if (!h->w_pre) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->w_pre), wp.size() * 4));
+        if (!h->b_pre) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->b_pre), bp.size() * 4));
+        B200_CUDA_OK(cudaMemcpy(h->w_pre, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+        B200_CUDA_OK(cudaMemcpy(h->b_pre, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+    }
     h->w_embed = take(static_cast<size_t>(C) * C * 7);
     if (launch_repack_weight(prec, h->m("decoder.backbone.embed.weight"), h->w_embed, C, C, 7, s)) return 1;
     const char* nets[4] = {"decoder.backbone.prior_net.0.", "decoder.backbone.prior_net.1.",

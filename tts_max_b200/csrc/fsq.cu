@@ -60,7 +60,7 @@ fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_t
     pdl_launch_dependents();
     pdl_wait();
     // channel block handled by this thread (grid.y covers channels > 2048 if ever needed)
-    const int c0 = (blockIdx.y * kFsqThreads + threadIdx.x) * kFsqChanPerThread;  // < channels (checked by the launcher)
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * kFsqChanPerThread;  // < channels (checked by the launcher)
 
     float w[kFsqChanPerThread][8];
     float b[kFsqChanPerThread];
@@ -207,15 +207,17 @@ int launch_typed(const void* ids, int id_type, const int32_t* row_tok, int rows,
                  const float* w_out, const float* b_out, int channels, void* out, int ld,
                  int* err_flag, cudaStream_t stream) {
     if (rows <= 0) return 0;
-    const int chan_blocks = (channels + kFsqThreads * kFsqChanPerThread - 1) /
-                            (kFsqThreads * kFsqChanPerThread);
+    // one thread per 8 channels: 256 threads for the 2048-wide codebook output, 128 for the folded
+    // 1024-wide one; wider outputs tile over grid.y
+    const int threads = channels / kFsqChanPerThread < kFsqThreads ? channels / kFsqChanPerThread : kFsqThreads;
+    const int chan_blocks = channels / (threads * kFsqChanPerThread);
     dim3 grid((rows + kFsqRowsPerBlock - 1) / kFsqRowsPerBlock, chan_blocks);
     if (id_type == 1)
-        B200_CUDA_OK(launch_kernel(fsq_lookup_kernel<OutT, long long>, grid, dim3(kFsqThreads), 0, stream,
+        B200_CUDA_OK(launch_kernel(fsq_lookup_kernel<OutT, long long>, grid, dim3(threads), 0, stream,
                                    static_cast<const long long*>(ids), row_tok, rows, w_out, b_out, channels,
                                    static_cast<OutT*>(out), ld, err_flag));
     else
-        B200_CUDA_OK(launch_kernel(fsq_lookup_kernel<OutT, int>, grid, dim3(kFsqThreads), 0, stream,
+        B200_CUDA_OK(launch_kernel(fsq_lookup_kernel<OutT, int>, grid, dim3(threads), 0, stream,
                                    static_cast<const int*>(ids), row_tok, rows, w_out, b_out, channels,
                                    static_cast<OutT*>(out), ld, err_flag));
     B200_CUDA_OK(cudaGetLastError());
@@ -227,7 +229,9 @@ int launch_typed(const void* ids, int id_type, const int32_t* row_tok, int rows,
 int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int rows,
                       const float* w_out, const float* b_out, int channels, void* out, int ld,
                       int out_prec, int* err_flag, cudaStream_t stream) {
-    B200_CHECK(channels % (kFsqChanPerThread * kFsqThreads) == 0, "fsq: channels must be a multiple of %d",
+    B200_CHECK(channels >= 256 && (channels % (kFsqChanPerThread * kFsqThreads) == 0 ||
+                                   (channels < kFsqChanPerThread * kFsqThreads && channels % 256 == 0)),
+               "fsq: channels (%d) must be 256..2048 in steps of 256, or a multiple of %d", channels,
                kFsqChanPerThread * kFsqThreads);
     if (out_prec < 0)
         return launch_typed<float>(ids, id_type, row_tok, rows, w_out, b_out, channels, out, ld,
