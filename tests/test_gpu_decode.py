@@ -55,6 +55,35 @@ def test_batched_forward_vs_reference_golden(gpu_decoders, golden, prec):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_frontend_fold_equals_lookup_plus_conv7(gpu_decoders, golden, prec):
+    """ids -> embed output as one folded 7-tap lookup (default) vs lookup + conv7 GEMM: the same
+    function, both within tolerance of the reference, the fp64-folded one at least as close; edge
+    frames (utterances of 1..7 tokens, where taps fall off the ends) included."""
+    from tts_max_b200 import _lib
+
+    d = gpu_decoders[prec]
+    lib = _lib.load()
+    ids = torch.from_numpy(golden["u37_ids"]).view(1, -1).cuda()
+    ref = torch.from_numpy(golden["u37_wav"])[0]
+    g = torch.Generator().manual_seed(321)
+    lens = [1, 2, 3, 4, 5, 6, 7, 40]
+    short = torch.randint(0, 65536, (sum(lens),), generator=g)
+    try:
+        _lib.check(lib.b200codec_set_frontend_fold(0))
+        gemm_wav = d(ids)[0, 0].cpu()
+        gemm_short = d.decode_packed_host(short, lens).clone()
+        _lib.check(lib.b200codec_set_frontend_fold(1))
+        fold_wav = d(ids)[0, 0].cpu()
+        fold_short = d.decode_packed_host(short, lens).clone()
+    finally:
+        _lib.check(lib.b200codec_set_frontend_fold(1))
+    check_wave(ref, gemm_wav, prec, "u37 lookup+conv7")
+    check_wave(ref, fold_wav, prec, "u37 folded front end")
+    assert O.snr_db(ref, fold_wav) >= O.snr_db(ref, gemm_wav) - 0.5
+    check_wave(gemm_short, fold_short, prec, "short utterances, folded vs lookup+conv7")
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
 def test_config1_vs_oracle(gpu_decoders, state_dict, prec):
     """BASELINE config 1: 4 clips x 5 s against the fp32 CPU oracle."""
     d = gpu_decoders[prec]

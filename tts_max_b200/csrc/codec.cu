@@ -25,6 +25,7 @@
 namespace b200 {
 
 int g_use_pdl = 1;
+static int g_frontend_fold = 1;  // ids -> embed output as one folded lookup (0: lookup + conv7 GEMM)
 static int g_zero_copy_out = 1;  // decode_host: write PCM directly into pinned host memory
 
 static thread_local char g_err[1024] = {0};
@@ -138,6 +139,8 @@ struct B200Codec {
     float* head_bias_pad = nullptr;
     float* w_pre = nullptr;  // fc_post_a o project_out folded: [C, 8] codebook projection ...
     float* b_pre = nullptr;  // ... and [C] bias (fp32)
+    float* m_fold = nullptr;   // embed o fc_post_a o project_out: [7][C][8] ...
+    float* cb_fold = nullptr;  // ... and the per-tap bias part [7][C]
     float2* twiddle = nullptr;
     float *rope_cos = nullptr, *rope_sin = nullptr;
 
@@ -736,20 +739,27 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
     const int C = h->C, prec = h->cfg.precision;
     const RowSpace& rs = h->rs;
     B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * h->gn_slots * rs.n_utts * 64, s));
-    {
-        // project_out (8 -> 2048, decoder.py:77) and fc_post_a (2048 -> 1024, decoder.py:79) are two
-        // linear maps back to back, so fc_post_a(project_out(code)) = W_pre code + b_pre with the
-        // [1024, 8] product folded in fp64 at load time: the same digit-unpack / 8-term lookup
-        // kernel as the stand-alone K1, one quarter of the bytes and no K = 2048 GEMM. Halo rows
-        // are written as zeros: this is the conv7 operand.
+    if (g_frontend_fold) {
+        // project_out (8 -> 2048, decoder.py:77), fc_post_a (2048 -> 1024, decoder.py:79) and the
+        // backbone's embed Conv1d (k = 7, decoder_modules.py:340,392) are linear maps back to back:
+        // the conv output is a 7-tap x 8-digit lookup with coefficients folded in fp64 at load time
+        // (see fsq_frontend_kernel). No 2048-wide intermediate, no K = 2048 / K = 7168 GEMM.
         Stage t(h, "fsq_lookup", s);
-        RUN(launch_fsq_lookup(ids_dev, id_type, rs.row_tok, rs.rows, h->w_pre, h->b_pre, C, h->xc, C, prec,
-                              h->err_flag_dev, s));
-    }
-    {
-        Stage t(h, "embed_conv7_gemm", s);
-        RUN(gemm(h, h->xc, C, h->w_embed, C, 7, h->x, true, C, C,
-                 h->m("decoder.backbone.embed.bias"), nullptr, kActNone, false, s));
+        RUN(launch_fsq_frontend(ids_dev, id_type, rs.row_tok, rs.rows, h->m_fold, h->cb_fold,
+                                h->m("decoder.backbone.embed.bias"), C, h->x, h->err_flag_dev, s));
+    } else {
+        {
+            // fc_post_a(project_out(code)) = W_pre code + b_pre: the same digit-unpack / 8-term lookup
+            // kernel as the stand-alone K1. Halo rows are written as zeros: this is the conv7 operand.
+            Stage t(h, "fsq_lookup", s);
+            RUN(launch_fsq_lookup(ids_dev, id_type, rs.row_tok, rs.rows, h->w_pre, h->b_pre, C, h->xc, C, prec,
+                                  h->err_flag_dev, s));
+        }
+        {
+            Stage t(h, "embed_conv7_gemm", s);
+            RUN(gemm(h, h->xc, C, h->w_embed, C, 7, h->x, true, C, C,
+                     h->m("decoder.backbone.embed.bias"), nullptr, kActNone, false, s));
+        }
     }
     // RMSNorm fusion (bf16 operands, CTA-pair GEMM): the GEMM that produces the residual stream x
     // also emits bf16(x) and per-row sum-of-squares partials; the norm weight lives in the columns
@@ -982,6 +992,8 @@ void b200codec_destroy(B200Codec* h) {
     if (h->plan_host) cudaFreeHost(h->plan_host);
     if (h->head_bias_pad) cudaFree(h->head_bias_pad);
     if (h->twiddle) cudaFree(h->twiddle);
+    if (h->m_fold) cudaFree(h->m_fold);
+    if (h->cb_fold) cudaFree(h->cb_fold);
     if (h->w_pre) cudaFree(h->w_pre);
     if (h->b_pre) cudaFree(h->b_pre);
     if (h->rope_cos) cudaFree(h->rope_cos);
@@ -1120,6 +1132,7 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
         B200_CUDA_OK(cudaMemcpy(bo.data(), h->m("decoder.quantizer.project_out.bias"), bo.size() * 4,
                                 cudaMemcpyDeviceToHost));
         std::vector<float> wp(static_cast<size_t>(C) * 8), bp(C);
+        std::vector<double> wp64(static_cast<size_t>(C) * 8), bp64(C);
         for (int c = 0; c < C; ++c) {
             double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             double b = bfc[c];
@@ -1129,9 +1142,41 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
                 for (int d = 0; d < 8; ++d) acc[d] += wv * wo[static_cast<size_t>(v) * 8 + d];
                 b += wv * bo[v];
             }
-            for (int d = 0; d < 8; ++d) wp[static_cast<size_t>(c) * 8 + d] = static_cast<float>(acc[d]);
+            for (int d = 0; d < 8; ++d) {
+                wp[static_cast<size_t>(c) * 8 + d] = static_cast<float>(acc[d]);
+                wp64[static_cast<size_t>(c) * 8 + d] = acc[d];
+            }
             bp[c] = static_cast<float>(b);
+            bp64[c] = b;
         }
+        // second fold: M[tap] = W_e[:, :, tap] W_pre, cb[tap] = W_e[:, :, tap] b_pre
+        std::vector<float> we(static_cast<size_t>(C) * C * 7);
+        B200_CUDA_OK(cudaMemcpy(we.data(), h->m("decoder.backbone.embed.weight"), we.size() * 4,
+                                cudaMemcpyDeviceToHost));
+        std::vector<float> mf(static_cast<size_t>(7) * C * 8), cbf(static_cast<size_t>(7) * C);
+        for (int c = 0; c < C; ++c) {
+            double acc[7][9];
+            for (int t = 0; t < 7; ++t)
+                for (int d = 0; d < 9; ++d) acc[t][d] = 0.0;
+            for (int k = 0; k < C; ++k) {
+                const float* wr = &we[(static_cast<size_t>(c) * C + k) * 7];
+                const double* pk = &wp64[static_cast<size_t>(k) * 8];
+                for (int t = 0; t < 7; ++t) {
+                    const double wv = wr[t];
+                    for (int d = 0; d < 8; ++d) acc[t][d] += wv * pk[d];
+                    acc[t][8] += wv * bp64[k];
+                }
+            }
+            for (int t = 0; t < 7; ++t) {
+                for (int d = 0; d < 8; ++d)
+                    mf[(static_cast<size_t>(t) * C + c) * 8 + d] = static_cast<float>(acc[t][d]);
+                cbf[static_cast<size_t>(t) * C + c] = static_cast<float>(acc[t][8]);
+            }
+        }
+        if (!h->m_fold) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->m_fold), mf.size() * 4));
+        if (!h->cb_fold) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->cb_fold), cbf.size() * 4));
+        B200_CUDA_OK(cudaMemcpy(h->m_fold, mf.data(), mf.size() * 4, cudaMemcpyHostToDevice));
+        B200_CUDA_OK(cudaMemcpy(h->cb_fold, cbf.data(), cbf.size() * 4, cudaMemcpyHostToDevice));
         if (!h->w_pre) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->w_pre), wp.size() * 4));
         if (!h->b_pre) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->b_pre), bp.size() * 4));
         B200_CUDA_OK(cudaMemcpy(h->w_pre, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
@@ -1323,6 +1368,11 @@ int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0;
 int b200codec_set_attention_impl(int impl) {
     B200_CHECK(impl == 0 || impl == 1, "attention impl must be 0 (tcgen05) or 1 (mma.sync)");
     g_attention_impl = impl;
+    return 0;
+}
+
+int b200codec_set_frontend_fold(int on) {
+    g_frontend_fold = on != 0;
     return 0;
 }
 

@@ -125,6 +125,103 @@ fsq_lookup_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_t
 }
 
 // ---------------------------------------------------------------------------
+// Fused front end: ids -> embed(fc_post_a(project_out(code)))  (decoder.py:77-79, decoder_modules.py:340,392)
+//
+// Nothing non-linear separates the codebook projection (8 -> 2048), fc_post_a (2048 -> 1024) and the
+// backbone's first Conv1d (k = 7, "same"): frame t of the conv output is a linear function of the
+// seven neighbouring codes,
+//   y_t[c] = b_e[c] + sum_{tap : frame t+tap-3 exists} ( cb[tap][c] + sum_d M[tap][c][d] * code_{t+tap-3}[d] )
+// with M[tap] = W_e[:, :, tap] W_fc W_out  ([1024, 8]) and cb[tap] = W_e[:, :, tap] (W_fc b_out + b_fc)
+// folded in fp64 at load time. Zero padding at the utterance edges drops the whole tap term (the
+// reference pads fc_post_a's OUTPUT with zeros, so the bias part disappears with it).
+// One thread owns one output channel (56 + 7 coefficients in registers) and streams a slab of
+// rows; the slab's codes (+3 rows each side) are decoded once into shared memory. Fixed
+// evaluation order (tap-major, digit-minor): batch-invariant. HBM-bound: 8 B in, 4 096 B out.
+constexpr int kFrontRows = 63;  // a multiple of the 7-row register window
+constexpr int kFrontThreads = 256;
+
+template <typename IdT>
+__global__ void __launch_bounds__(kFrontThreads)
+fsq_frontend_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_tok, int rows,
+                    const float* __restrict__ m_fold,   // [7][C][8]
+                    const float* __restrict__ cb_fold,  // [7][C]
+                    const float* __restrict__ b_embed,  // [C]
+                    int C, float* __restrict__ x, int* __restrict__ err_flag) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int c = blockIdx.y * kFrontThreads + threadIdx.x;
+    float m[7][8], cb[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+        const float4* mr = reinterpret_cast<const float4*>(m_fold + (static_cast<size_t>(t) * C + c) * 8);
+        const float4 lo = __ldg(mr), hi = __ldg(mr + 1);
+        m[t][0] = lo.x; m[t][1] = lo.y; m[t][2] = lo.z; m[t][3] = lo.w;
+        m[t][4] = hi.x; m[t][5] = hi.y; m[t][6] = hi.z; m[t][7] = hi.w;
+        cb[t] = __ldg(cb_fold + static_cast<size_t>(t) * C + c);
+    }
+    const float be = __ldg(b_embed + c);
+
+    // codes of rows [r_begin - 3, r_end + 3): eight digits + a 0/1 "frame exists" factor that
+    // multiplies the tap's bias part, so edge handling needs no branch (absent frames have zero codes)
+    __shared__ __align__(16) float s_code[kFrontRows + 6][12];
+    const int r_begin = blockIdx.x * kFrontRows;
+    const int r_end = min(r_begin + kFrontRows, rows);
+    for (int i = threadIdx.x; i < kFrontRows + 6; i += kFrontThreads) {
+        const int r = r_begin - 3 + i;
+        int valid = 0;
+        unsigned uid = 0;
+        if (r >= 0 && r < rows) {
+            const int tok = row_tok ? row_tok[r] : r;
+            if (tok >= 0) {
+                const long long id = static_cast<long long>(ids[tok]);
+                if ((id < 0 || id > 65535) && blockIdx.y == 0) atomicExch(err_flag, 1);
+                uid = static_cast<unsigned>(id) & 0xFFFFu;
+                valid = 1;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            s_code[i][d] = valid ? static_cast<float>(static_cast<int>((uid >> (2 * d)) & 3) - 2) * 0.5f : 0.f;
+        s_code[i][8] = valid ? 1.f : 0.f;
+        s_code[i][9] = s_code[i][10] = s_code[i][11] = 0.f;
+    }
+    __syncthreads();
+    // Sliding 7-row window in registers: code row n of the slab lives in slot n % 7, so every row is
+    // read from shared memory once (3 loads) instead of once per tap (21).
+    float cw[7][9];
+    auto load_slot = [&](int slot, int n) {
+        const float4 lo = *reinterpret_cast<const float4*>(&s_code[n][0]);
+        const float4 hi = *reinterpret_cast<const float4*>(&s_code[n][4]);
+        cw[slot][0] = lo.x; cw[slot][1] = lo.y; cw[slot][2] = lo.z; cw[slot][3] = lo.w;
+        cw[slot][4] = hi.x; cw[slot][5] = hi.y; cw[slot][6] = hi.z; cw[slot][7] = hi.w;
+        cw[slot][8] = s_code[n][8];
+    };
+#pragma unroll
+    for (int n = 0; n < 6; ++n) load_slot(n, n);
+    const int n_rows = r_end - r_begin;
+    for (int rr = 0; rr < n_rows; rr += 7) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            load_slot((j + 6) % 7, rr + j + 6);  // row r + 3 of output row r = r_begin + rr + j
+            // five independent chains (digit pairs + bias), tap-major inside each: fixed order
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ab = 0.f;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                const float* cv = cw[(j + t) % 7];
+                a0 = fmaf(cv[1], m[t][1], fmaf(cv[0], m[t][0], a0));
+                a1 = fmaf(cv[3], m[t][3], fmaf(cv[2], m[t][2], a1));
+                a2 = fmaf(cv[5], m[t][5], fmaf(cv[4], m[t][4], a2));
+                a3 = fmaf(cv[7], m[t][7], fmaf(cv[6], m[t][6], a3));
+                ab = fmaf(cv[8], cb[t], ab);
+            }
+            const float y = (be + ab) + ((a0 + a1) + (a2 + a3));
+            if (rr + j < n_rows)  // halo rows: zeros
+                x[static_cast<size_t>(r_begin + rr + j) * C + c] = cw[(j + 3) % 7][8] != 0.f ? y : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // FSQ quantise (encode direction): the mirror image of the lookup above.
 //
 // Replaces vector_quantize_pytorch.ResidualFSQ.forward as called by Encoder.quantize
@@ -244,6 +341,23 @@ int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int 
                                     err_flag, stream);
     set_error("fsq: unsupported output precision %d", out_prec);
     return 1;
+}
+
+int launch_fsq_frontend(const void* ids, int id_type, const int32_t* row_tok, int rows, const float* m_fold,
+                        const float* cb_fold, const float* b_embed, int C, float* x, int* err_flag,
+                        cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    B200_CHECK(C % kFrontThreads == 0, "fsq front end: channels must be a multiple of %d", kFrontThreads);
+    dim3 grid((rows + kFrontRows - 1) / kFrontRows, C / kFrontThreads);
+    if (id_type == 1)
+        B200_CUDA_OK(launch_kernel(fsq_frontend_kernel<long long>, grid, dim3(kFrontThreads), 0, stream,
+                                   static_cast<const long long*>(ids), row_tok, rows, m_fold, cb_fold, b_embed, C, x,
+                                   err_flag));
+    else
+        B200_CUDA_OK(launch_kernel(fsq_frontend_kernel<int>, grid, dim3(kFrontThreads), 0, stream,
+                                   static_cast<const int*>(ids), row_tok, rows, m_fold, cb_fold, b_embed, C, x,
+                                   err_flag));
+    return 0;
 }
 
 int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in, const float* b_in,

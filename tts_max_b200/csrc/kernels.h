@@ -44,6 +44,11 @@ constexpr int kIstftOutHops = 12;   // output hops per ISTFT CTA (+4 halo frames
 int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int rows,
                       const float* w_out /*[C,8]*/, const float* b_out /*[C]*/, int channels,
                       void* out, int ld, int out_prec, int* err_flag, cudaStream_t stream);
+// fused front end: ids -> embed(fc_post_a(project_out(code))) as one 7-tap x 8-digit lookup
+// (m_fold [7][C][8], cb_fold [7][C], b_embed [C]; x fp32 [rows, C], halo rows zero)
+int launch_fsq_frontend(const void* ids, int id_type, const int32_t* row_tok, int rows, const float* m_fold,
+                        const float* cb_fold, const float* b_embed, int C, float* x, int* err_flag,
+                        cudaStream_t stream);
 // encode direction (encoder.py:73-78): features [n_tokens, ld] fp32 -> ids (id_type 0: int32, 1: int64);
 // z_out (optional) receives the eight projected values per token
 int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in, const float* b_in,
