@@ -530,6 +530,7 @@ struct NormFuse {
     const float* ss_in = nullptr;  // consume: scale rows by rsqrt(mean(x^2) + eps)
     void* out16 = nullptr;         // produce: 16-bit copy of the fp32 result ...
     float* ss_out = nullptr;       // ... and its per-row sum-of-squares partials
+    double* gn_stats = nullptr;    // produce: GroupNorm statistics of the fp32 result (N == 1024 only)
 };
 
 int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
@@ -558,11 +559,18 @@ int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, v
     c.out16 = nf.out16;
     c.ld16 = h->C;
     c.ss_out = nf.ss_out;
+    c.gn_stats = nf.gn_stats;
+    c.gn_row_utt = h->rs.row_utt;
     return launch_gemm(c, s);
 }
 
 // ResnetBlock (decoder_modules.py:201-223) on one row space at C channels:
 //   x <- x + conv2(swish(GN2(conv1(swish(GN1(x))))))
+static bool g_gn_in_gemm = true;  // GroupNorm statistics reduced in the producing GEMM's epilogue
+static bool gn_stats_in_gemm(int rows, int C) {
+    return g_gn_in_gemm && C == 1024 && gemm_uses_cta_pairs(rows, C);
+}
+
 struct ResCtx {
     const RowSpace* rs;
     int C;
@@ -572,8 +580,11 @@ struct ResCtx {
     bool mask_out;   // write zeros on halo rows of x / out16 (x feeds a (transposed) conv directly)
 };
 
+// gn1_done: the producer of x already reduced this block's first GroupNorm statistics into its
+// slot (a GEMM epilogue, see NormFuse::gn_stats). next_gn: where conv2 should leave the statistics
+// of the block output for the GroupNorm that consumes it next (nullptr: nobody).
 int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stats_slot, cudaStream_t s,
-                    const NormFuse& nf) {
+                    const NormFuse& nf, bool gn1_done = false, double* next_gn = nullptr) {
     const int C = cx.C, prec = h->cfg.precision;
     const RowSpace& rs = *cx.rs;
     double* st1 = h->gn_stats + static_cast<size_t>(stats_slot) * rs.n_utts * 64;
@@ -606,35 +617,44 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
         c.out16 = f.out16;
         c.ld16 = C;
         c.ss_out = f.ss_out;
+        c.gn_stats = f.gn_stats;
+        c.gn_row_utt = rs.row_utt;
         return launch_gemm(c, s);
     };
+    // the conv GEMMs reduce the statistics of what they write when a chunk of their epilogue is a
+    // group (C == 1024 on the CTA-pair kernel); otherwise a stand-alone pass over the activations does
+    const bool fused_stats = gn_stats_in_gemm(rs.rows, C);
     {
         Stage t(h, "groupnorm_swish", s);
-        RUN(launch_groupnorm_stats(cx.x, rs, C, st1, s));
+        if (!gn1_done) RUN(launch_groupnorm_stats(cx.x, rs, C, st1, s));
         RUN(launch_groupnorm_apply_swish(prec, cx.x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, cx.an, s, mr1));
         h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
-        RUN(conv3(cx.an, w.w1, cx.hb, w.b1, nullptr, false, NormFuse()));
+        NormFuse f1;
+        if (fused_stats) f1.gn_stats = st2;
+        RUN(conv3(cx.an, w.w1, cx.hb, w.b1, nullptr, false, f1));
     }
     {
         Stage t(h, "groupnorm_swish", s);
-        RUN(launch_groupnorm_stats(cx.hb, rs, C, st2, s));
+        if (!fused_stats) RUN(launch_groupnorm_stats(cx.hb, rs, C, st2, s));
         RUN(launch_groupnorm_apply_swish(prec, cx.hb, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, cx.an, s, mr2));
         h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
-        RUN(conv3(cx.an, w.w2, cx.x, w.b2, cx.x, cx.mask_out, nf));
+        NormFuse f2 = nf;
+        if (fused_stats) f2.gn_stats = next_gn;
+        RUN(conv3(cx.an, w.w2, cx.x, w.b2, cx.x, cx.mask_out, f2));
     }
     return 0;
 }
 
 int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t s,
-                 const NormFuse& nf = NormFuse()) {
+                 const NormFuse& nf = NormFuse(), bool gn1_done = false, double* next_gn = nullptr) {
     ResCtx cx{&h->rs, h->C, h->x, h->hbuf, h->an, false};
-    return resnet_block_ex(h, cx, w, stats_slot, s, nf);
+    return resnet_block_ex(h, cx, w, stats_slot, s, nf, gn1_done, next_gn);
 }
 
 // UpSamplerBlock.forward (upsampler.py:62-69): per stage, ConvTranspose1d as `stride` row-shifted convs
@@ -772,8 +792,12 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
         produce.ss_out = h->ss;
         consume.ss_in = h->ss;
     }
-    if (resnet_block(h, h->res[0], 0, s)) return 1;
-    if (resnet_block(h, h->res[1], 2, s, produce)) return 1;
+    // GroupNorm statistics slot k (k = 2 * block + {0: norm1, 1: norm2}) of utterance u, group g:
+    // gn_stats[((k * n_utts + u) * 32 + g) * 2 + {sum, sumsq}]
+    const bool gn_fused = gn_stats_in_gemm(rs.rows, C);
+    auto gn_slot = [&](int k) { return gn_fused ? h->gn_stats + static_cast<size_t>(k) * rs.n_utts * 64 : nullptr; };
+    if (resnet_block(h, h->res[0], 0, s, NormFuse(), false, gn_slot(2))) return 1;
+    if (resnet_block(h, h->res[1], 2, s, produce, gn_fused, nullptr)) return 1;
     for (int l = 0; l < h->L; ++l) {
         const LayerW& w = h->layers[l];
         const bool last = l + 1 == h->L;
@@ -806,12 +830,16 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
         }
         {
             Stage t(h, "fc2_gemm", s);
-            RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s,
-                     last ? NormFuse() : produce));
+            NormFuse f2 = produce;
+            if (last) {
+                f2 = NormFuse();
+                f2.gn_stats = gn_slot(4);  // post_net.0's first GroupNorm reads this x
+            }
+            RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s, f2));
         }
     }
-    if (resnet_block(h, h->res[2], 4, s)) return 1;
-    if (resnet_block(h, h->res[3], 6, s)) return 1;
+    if (resnet_block(h, h->res[2], 4, s, NormFuse(), gn_fused && h->L > 0, gn_slot(6))) return 1;
+    if (resnet_block(h, h->res[3], 6, s, NormFuse(), gn_fused, nullptr)) return 1;
     {
         Stage t(h, "layernorm", s);
         // with an upsampler the LayerNorm output feeds a transposed conv: halo rows must be zero

@@ -273,6 +273,11 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     B200_CHECK(c.residual == nullptr || gemm_kind(c) != kGemm2Cta ||
                    ((reinterpret_cast<uintptr_t>(c.residual) & 31) == 0 && c.ld_res % 8 == 0),
                "gemm: the residual must be 32-byte aligned with a row pitch that is a multiple of 8");
+    p.gn_stats = c.gn_stats;
+    p.gn_row_utt = c.gn_row_utt;
+    B200_CHECK(c.gn_stats == nullptr ||
+                   (gemm_kind(c) == kGemm2Cta && c.out_fp32 && c.n_store == 1024 && c.gn_row_utt != nullptr),
+               "gemm: GroupNorm statistics need the CTA-pair kernel, fp32 output, N == 1024 and a row -> utterance map");
     p.has32 = c.out_fp32 ? 1 : 0;
     p.has16 = (!c.out_fp32 || c.out16 != nullptr) ? 1 : 0;
     if (gemm_kind(c) == kGemm2Cta) {
@@ -290,8 +295,14 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
         } else {
             if (make_tmap_box(&to16, c.out, dt16, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
         }
-        if (c.precision == kPrecBf16) return launch_gemm_tc05_2cta<__nv_bfloat16>(ta, tb, to32, to16, p, stream);
-        return launch_gemm_tc05_2cta<__half>(ta, tb, to32, to16, p, stream);
+        if (p.gn_stats != nullptr) {
+            if (c.precision == kPrecBf16)
+                return launch_gemm_tc05_2cta<__nv_bfloat16, true>(ta, tb, to32, to16, p, stream);
+            return launch_gemm_tc05_2cta<__half, true>(ta, tb, to32, to16, p, stream);
+        }
+        if (c.precision == kPrecBf16)
+            return launch_gemm_tc05_2cta<__nv_bfloat16, false>(ta, tb, to32, to16, p, stream);
+        return launch_gemm_tc05_2cta<__half, false>(ta, tb, to32, to16, p, stream);
     }
     if (c.precision == kPrecBf16) return dispatch<__nv_bfloat16>(c, ta, tb, p, wide, stream);
     return dispatch<__half>(c, ta, tb, p, wide, stream);

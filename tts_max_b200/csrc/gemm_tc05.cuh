@@ -56,6 +56,10 @@ struct GemmParams {
     // CTA-pair kernel: which outputs exist (their addresses travel in tensor maps)
     int has32;             // fp32 `out` (+ optional residual)
     int has16;             // 16-bit `out` (has32 == 0) or the 16-bit copy `out16` (has32 == 1)
+    // CTA-pair kernel, GroupNorm(32 groups) statistics of the fp32 result (N == 1024: a 32-column
+    // epilogue chunk is one group): stats[(utt * 32 + group) * 2 + {0, 1}] += {sum, sum of squares}
+    double* gn_stats;            // nullptr = off
+    const int32_t* gn_row_utt;   // [M] utterance of each row, -1 on halo rows
 #ifdef B200_GEMM_TRACE
     unsigned long long* trace;  // tools/gemm_trace.cu only: [gridDim.x][128] timestamps
 #endif

@@ -125,7 +125,9 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
 
 // tmap_o32: fp32 [M, n_store] output, box 32 x 32, SWIZZLE_128B (used when p.has32);
 // tmap_o16: 16-bit [M, n_store] output or operand copy, box 32 x 32, SWIZZLE_64B (p.has16).
-template <typename InT>
+// kGnStats: the instantiation that also reduces GroupNorm statistics (p.gn_stats), kept apart so the
+// extra registers do not touch the common kernel.
+template <typename InT, bool kGnStats>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
@@ -294,6 +296,16 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const bool row_ok = row < p.M;
             const bool row_zero = row_ok && p.row_valid != nullptr && p.row_valid[row] == 0;
             const bool any_zero = __any_sync(0xffffffffu, row_zero);  // halo rows are rare
+            int gn_utt = -1;         // this lane's utterance (GroupNorm statistics), -1: not a frame
+            bool gn_uniform = true;  // every frame row of the warp belongs to one utterance
+            int gn_u0 = -1;
+            if constexpr (kGnStats) {
+                if (row_ok) gn_utt = p.gn_row_utt[row];
+                gn_u0 = gn_utt;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) gn_u0 = max(gn_u0, __shfl_xor_sync(0xffffffffu, gn_u0, o));
+                gn_uniform = __all_sync(0xffffffffu, gn_utt < 0 || gn_utt == gn_u0);
+            }
             const int ncol0 = n_blk * BLOCK_N + hh * 128;
             // this lane's residual row: 128 contiguous bytes per chunk, fetched as whole sectors
             const float* res_row = has_res && row_ok
@@ -381,6 +393,36 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = row_zero ? 0.f : v[j];
                 }
+                if constexpr (kGnStats) {
+                    // GroupNorm statistics of this chunk = one group of 32 channels: fp32 per row in
+                    // a fixed order (position-independent), fp64 across rows (order-insensitive at
+                    // fp32 resolution), so the statistics do not depend on the batch an utterance is in
+                    float gs = 0.f, gq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        gs += v[j];
+                        gq = fmaf(v[j], v[j], gq);
+                    }
+                    if (gn_utt < 0) gs = gq = 0.f;
+                    const int group = n0 >> 5;
+                    if (gn_uniform) {
+                        if (gn_u0 >= 0) {
+                            double ds = static_cast<double>(gs), dq = static_cast<double>(gq);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                                dq += __shfl_xor_sync(0xffffffffu, dq, o);
+                            }
+                            if (lane == 0) {
+                                atomicAdd(p.gn_stats + (static_cast<size_t>(gn_u0) * 32 + group) * 2 + 0, ds);
+                                atomicAdd(p.gn_stats + (static_cast<size_t>(gn_u0) * 32 + group) * 2 + 1, dq);
+                            }
+                        }
+                    } else if (gn_utt >= 0) {  // a warp that straddles two utterances (rare)
+                        atomicAdd(p.gn_stats + (static_cast<size_t>(gn_utt) * 32 + group) * 2 + 0, static_cast<double>(gs));
+                        atomicAdd(p.gn_stats + (static_cast<size_t>(gn_utt) * 32 + group) * 2 + 1, static_cast<double>(gq));
+                    }
+                }
                 // the boxes this chunk writes were last read by the stores of chunk g-1 (fp32)
                 // and g-2 (16-bit); those are normally long done
                 if (lane == 0) bulk_wait_group_read<0>();
@@ -447,10 +489,10 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
-template <typename InT>
+template <typename InT, bool kGnStats>
 int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to32,
                           const CUtensorMap& to16, const GemmParams& p, cudaStream_t stream) {
-    auto kern = gemm_tc05_2cta_kernel<InT>;
+    auto kern = gemm_tc05_2cta_kernel<InT, kGnStats>;
     static PerDeviceOnce once;
     if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

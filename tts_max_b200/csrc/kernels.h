@@ -115,6 +115,10 @@ struct GemmCall {
     // when null they are encoded on the fly.
     const void* tmap_a = nullptr;
     const void* tmap_b = nullptr;
+    // GroupNorm(32) statistics of the fp32 result, reduced in the epilogue (CTA-pair kernel, N == 1024):
+    // gn_stats[(utt * 32 + group) * 2 + {0, 1}] += {sum, sum of squares}; gn_row_utt[row] = utterance or -1
+    double* gn_stats = nullptr;
+    const int32_t* gn_row_utt = nullptr;
 };
 constexpr size_t kTmapBytes = 128;
 int launch_gemm(const GemmCall& c, cudaStream_t stream);
