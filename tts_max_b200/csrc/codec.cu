@@ -628,7 +628,6 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
         Stage t(h, "groupnorm_swish", s);
         if (!gn1_done) RUN(launch_groupnorm_stats(cx.x, rs, C, st1, s));
         RUN(launch_groupnorm_apply_swish(prec, cx.x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, cx.an, s, mr1));
-        h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);
@@ -640,7 +639,6 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
         Stage t(h, "groupnorm_swish", s);
         if (!fused_stats) RUN(launch_groupnorm_stats(cx.hb, rs, C, st2, s));
         RUN(launch_groupnorm_apply_swish(prec, cx.hb, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, cx.an, s, mr2));
-        h->launches++;
     }
     {
         Stage t(h, "conv3_gemm", s);

@@ -173,28 +173,14 @@ groupnorm_stats_kernel(const float* __restrict__ x, const int4* __restrict__ wor
     }
 }
 
-// (sum, sumsq) fp64 -> (mean, rstd) fp32 per (utterance, group); one warp per utterance
-__global__ void groupnorm_finalize_kernel(const double* __restrict__ stats,
-                                          const int32_t* __restrict__ utt_len, int group_size,
-                                          float eps, float2* __restrict__ mean_rstd) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int u = blockIdx.x, g = threadIdx.x;  // 32 groups
-    const double cnt = static_cast<double>(utt_len[u]) * group_size;
-    const double m = stats[(static_cast<size_t>(u) * 32 + g) * 2 + 0] / cnt;
-    double var = stats[(static_cast<size_t>(u) * 32 + g) * 2 + 1] / cnt - m * m;
-    var = var < 0.0 ? 0.0 : var;
-    mean_rstd[u * 32 + g] = make_float2(static_cast<float>(m),
-                                        static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
-}
-
 // y = swish((x - mean) * rstd * gamma + beta) -> operand dtype; halo rows are written as zeros
 // (the conv that follows reads them as its padding). DIM / 8 threads per row, 8 channels per thread:
 // 2 x 128-bit loads, one 128-bit store; a 256-thread CTA streams 2048 / DIM rows per iteration.
 template <typename OutT, int DIM>
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
-                             int rows, const float2* __restrict__ mean_rstd,
+                             int rows, const double* __restrict__ stats,
+                             const int32_t* __restrict__ utt_len, float eps,
                              const float* __restrict__ gamma, const float* __restrict__ beta,
                              OutT* __restrict__ out) {
     pdl_launch_dependents();
@@ -214,11 +200,26 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
         g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
         b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
     }
-    for (int r = blockIdx.x * kRows + sub; r < rows; r += gridDim.x * kRows) {
+    // a CTA walks a contiguous slab of rows, so (mean, rstd) of (utterance, group) -- fp64 from the
+    // accumulated (sum, sumsq), exactly what the former finalize kernel computed -- is refreshed
+    // only when the utterance changes
+    const int slab = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_lo = blockIdx.x * slab;
+    const int r_hi = min(r_lo + slab, rows);
+    int cur_u = -1;
+    float2 mr = make_float2(0.f, 0.f);
+    for (int r = r_lo + sub; r < r_hi; r += kRows) {
         const int u = row_utt[r];
         uint4 packed = make_uint4(0u, 0u, 0u, 0u);
         if (u >= 0) {
-            const float2 mr = __ldg(mean_rstd + u * 32 + group);
+            if (u != cur_u) {
+                cur_u = u;
+                const double cnt = static_cast<double>(utt_len[u]) * (DIM / 32);
+                const double m = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 0] / cnt;
+                double var = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 1] / cnt - m * m;
+                var = var < 0.0 ? 0.0 : var;
+                mr = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+            }
             const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * DIM + c0);
             const float4 v0 = xp[0], v1 = xp[1];
             float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -249,18 +250,17 @@ int launch_gn_typed(int prec, const float* x, const RowSpace& rs, const double* 
         return 0;
     }
     if (rs.rows <= 0) return 0;
-    B200_CUDA_OK(launch_kernel(groupnorm_finalize_kernel, dim3(rs.n_utts), dim3(32), 0, stream, stats, rs.utt_len,
-                               DIM / 32, eps, mean_rstd));
+    (void)mean_rstd;
     constexpr int kRows = kGnThreads / (DIM / 8);
     int grid = (rs.rows + kRows - 1) / kRows;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     if (prec == kPrecBf16)
         B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__nv_bfloat16, DIM>, dim3(grid), dim3(kGnThreads), 0,
-                                   stream, x, rs.row_utt, rs.rows, static_cast<const float2*>(mean_rstd), gamma,
+                                   stream, x, rs.row_utt, rs.rows, stats, rs.utt_len, eps, gamma,
                                    beta, static_cast<__nv_bfloat16*>(out)));
     else if (prec == kPrecFp16)
         B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__half, DIM>, dim3(grid), dim3(kGnThreads), 0, stream,
-                                   x, rs.row_utt, rs.rows, static_cast<const float2*>(mean_rstd), gamma, beta,
+                                   x, rs.row_utt, rs.rows, stats, rs.utt_len, eps, gamma, beta,
                                    static_cast<__half*>(out)));
     else {
         set_error("groupnorm: unsupported precision %d", prec);
