@@ -390,7 +390,10 @@ def run_ours(args):
 
         roofline["hbm_kernels"] = [
             hbm_entry("fsq_frontend_kernel (project_out o fc_post_a o embed conv7 folded: 8 B id in, 1024 x 4 B out)", "fsq_lookup", 8 + 4096, 1),
-            hbm_entry("groupnorm stats + finalize + apply_swish (2 x 4096 B in, 2048 B out)", "groupnorm_swish", 2 * 4096 + 2048, 8),
+            # 8 apply passes (4096 B in, 2048 B out) + 1 stand-alone statistics pass (4096 B in); the other
+            # seven GroupNorms get their statistics from the producing GEMM's epilogue
+            hbm_entry("groupnorm_apply_swish x8 + groupnorm_stats x1 (per apply: 4096 B in, 2048 B out)", "groupnorm_swish",
+                      (8 * (4096 + 2048) + 4096) / 8, 8),
             hbm_entry("rownorm_kernel / LayerNorm (4096 B in, 2048 B out)", "layernorm", 4096 + 2048, 1),
             hbm_entry("istft_kernel (1282 x 4 B in, 320 x 4 B out; instruction-bound in practice)", "istft", 5128 + 1280, 1),
         ]
