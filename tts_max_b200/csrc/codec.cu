@@ -129,7 +129,6 @@ struct B200Codec {
 
     // prepared weights
     DevBuf wbuf;        // one slab for all operand-dtype weights
-    void* w_fc = nullptr;
     void* w_embed = nullptr;
     ResBlockW res[4];
     LayerW layers[64];
@@ -147,7 +146,7 @@ struct B200Codec {
     // workspace (grow-only)
     DevBuf ws;
     int ws_rows = 0;
-    void *a0, *xc, *an, *qkv, *y, *f, *xb;  // operand dtype
+    void *xc, *an, *qkv, *y, *f, *xb;  // operand dtype
     float *x, *hbuf, *ho, *ss;
     // upsampler stage i lives in row space plan[i + 1] at up[i].Cout channels
     float *u_x[kMaxUp], *u_h[kMaxUp];
@@ -439,10 +438,10 @@ int ensure_workspace(B200Codec* h, int rows) {
     const size_t C = h->C;
     auto al = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
     const size_t Rlast = R * h->total_up;  // rows of the last (upsampled) row space
-    size_t sz_a0 = 0 /* the 2048-wide FSQ output no longer exists: folded into fc_post_a */, sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
+    size_t sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
            sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(Rlast * h->head_ld * 4);
     size_t sz_ss = al(R * 8 * 4);
-    size_t total = sz_a0 + 4 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho + sz_ss;
+    size_t total = 4 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho + sz_ss;
     size_t up_rows[kMaxUp], sz_up32[kMaxUp], sz_up16[kMaxUp];
     {
         size_t f = 1;
@@ -460,7 +459,6 @@ int ensure_workspace(B200Codec* h, int rows) {
     if (h->ws.ensure(total)) return 1;
     B200_CUDA_OK(cudaMemset(h->ws.p, 0, h->ws.bytes));  // no NaN garbage in halo rows
     uint8_t* p = h->ws.as<uint8_t>();
-    h->a0 = p; p += sz_a0;
     h->xc = p; p += sz_c;
     h->an = p; p += sz_c;
     h->y = p; p += sz_c;
@@ -589,9 +587,6 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
     const RowSpace& rs = *cx.rs;
     double* st1 = h->gn_stats + static_cast<size_t>(stats_slot) * rs.n_utts * 64;
     double* st2 = st1 + static_cast<size_t>(rs.n_utts) * 64;
-    float2* mr_base = reinterpret_cast<float2*>(h->gn_stats + static_cast<size_t>(h->gn_slots) * rs.n_utts * 64);
-    float2* mr1 = mr_base + static_cast<size_t>(stats_slot) * rs.n_utts * 32;
-    float2* mr2 = mr1 + static_cast<size_t>(rs.n_utts) * 32;
     auto conv3 = [&](const void* a, const void* wt, float* out, const float* bias, const float* residual,
                      bool mask, const NormFuse& f) {
         GemmCall c;
@@ -627,7 +622,7 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
     {
         Stage t(h, "groupnorm_swish", s);
         if (!gn1_done) RUN(launch_groupnorm_stats(cx.x, rs, C, st1, s));
-        RUN(launch_groupnorm_apply_swish(prec, cx.x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, cx.an, s, mr1));
+        RUN(launch_groupnorm_apply_swish(prec, cx.x, rs, C, st1, w.gn1_w, w.gn1_b, 1e-6f, cx.an, s));
     }
     {
         Stage t(h, "conv3_gemm", s);
@@ -638,7 +633,7 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
     {
         Stage t(h, "groupnorm_swish", s);
         if (!fused_stats) RUN(launch_groupnorm_stats(cx.hb, rs, C, st2, s));
-        RUN(launch_groupnorm_apply_swish(prec, cx.hb, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, cx.an, s, mr2));
+        RUN(launch_groupnorm_apply_swish(prec, cx.hb, rs, C, st2, w.gn2_w, w.gn2_b, 1e-6f, cx.an, s));
     }
     {
         Stage t(h, "conv3_gemm", s);
@@ -1111,7 +1106,7 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     const int C = h->C, V = h->V, L = h->L, prec = h->cfg.precision;
     const size_t es = operand_bytes(prec);
     const size_t n_head = static_cast<size_t>(h->n_fft + 2) * C;
-    size_t elems = static_cast<size_t>(C) * V + static_cast<size_t>(C) * C * 7 +
+    size_t elems = static_cast<size_t>(C) * C * 7 +
                    8 * static_cast<size_t>(C) * C * 3 +
                    static_cast<size_t>(L) * (3ull * C * C + 1ull * C * C + 8ull * C * C) + n_head;
     for (int i = 0; i < h->n_up; ++i) {
@@ -1146,8 +1141,6 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     float* scratch = nullptr;
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&scratch), 3ull * C * C * sizeof(float)));
 
-    h->w_fc = take(static_cast<size_t>(C) * V);  // 16-bit fc_post_a operand (b200codec_gemm parity tests)
-    if (launch_repack_weight(prec, h->m("fc_post_a.weight"), h->w_fc, C, V, 1, s)) return 1;
     {
         // W_pre = W_fc W_out, b_pre = W_fc b_out + b_fc (fp64 on the host, stored fp32)
         std::vector<float> wfc(static_cast<size_t>(C) * V), bfc(C), wo(static_cast<size_t>(V) * 8), bo(V);
@@ -1531,13 +1524,12 @@ int b200codec_groupnorm_swish(int precision, const float* x_dev, const float* ga
     if (tp.build(seqlens_host, n_utts, s)) return 1;
     double* stats = nullptr;
     const size_t bytes = sizeof(double) * 64 * static_cast<size_t>(n_utts);
-    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stats), bytes + sizeof(float2) * 32 * n_utts));
-    float2* mean_rstd = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats) + bytes);
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stats), bytes));
     int rc = 0;
     if (cudaMemsetAsync(stats, 0, bytes, s) != cudaSuccess) rc = 1;
     if (!rc) rc = launch_groupnorm_stats(x_dev, tp.rs, dim, stats, s);
     if (!rc) rc = launch_groupnorm_apply_swish(precision, x_dev, tp.rs, dim, stats, gamma_dev,
-                                               beta_dev, eps, out_dev, s, mean_rstd);
+                                               beta_dev, eps, out_dev, s);
     cudaStreamSynchronize(s);
     cudaFree(stats);
     return rc;

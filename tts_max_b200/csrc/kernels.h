@@ -64,10 +64,10 @@ int launch_layernorm(int prec, const float* x, const float* w, const float* b, i
 // stats: double [n_utts][32][2] (sum, sumsq), must be zero on entry
 int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
                            cudaStream_t stream);
-// mean_rstd: scratch float2 [n_utts][32] filled by a finalize kernel from `stats`
+// mean / rstd per (utterance, group) are formed from `stats` (fp64 sums) inside the kernel
 int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, int dim,
                                  const double* stats, const float* gamma, const float* beta,
-                                 float eps, void* out, cudaStream_t stream, float2* mean_rstd);
+                                 float eps, void* out, cudaStream_t stream);
 
 // ---- attention.cu ----
 int launch_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,

@@ -239,7 +239,7 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
 
 template <int DIM>
 int launch_gn_typed(int prec, const float* x, const RowSpace& rs, const double* stats, const float* gamma,
-                    const float* beta, float eps, void* out, cudaStream_t stream, float2* mean_rstd,
+                    const float* beta, float eps, void* out, cudaStream_t stream,
                     bool stats_only, double* stats_out) {
     if (stats_only) {
         if (rs.n_attn_work <= 0) return 0;
@@ -250,7 +250,6 @@ int launch_gn_typed(int prec, const float* x, const RowSpace& rs, const double* 
         return 0;
     }
     if (rs.rows <= 0) return 0;
-    (void)mean_rstd;
     constexpr int kRows = kGnThreads / (DIM / 8);
     int grid = (rs.rows + kRows - 1) / kRows;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
@@ -271,11 +270,11 @@ int launch_gn_typed(int prec, const float* x, const RowSpace& rs, const double* 
 
 int launch_gn_dispatch(int dim, int prec, const float* x, const RowSpace& rs, const double* stats,
                        const float* gamma, const float* beta, float eps, void* out, cudaStream_t stream,
-                       float2* mean_rstd, bool stats_only, double* stats_out) {
+                       bool stats_only, double* stats_out) {
     switch (dim) {
-        case 1024: return launch_gn_typed<1024>(prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, stats_only, stats_out);
-        case 512: return launch_gn_typed<512>(prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, stats_only, stats_out);
-        case 256: return launch_gn_typed<256>(prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, stats_only, stats_out);
+        case 1024: return launch_gn_typed<1024>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
+        case 512: return launch_gn_typed<512>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
+        case 256: return launch_gn_typed<256>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
         default:
             set_error("groupnorm: dim %d is not instantiated (1024, 512, 256)", dim);
             return 1;
@@ -296,14 +295,13 @@ int launch_layernorm(int prec, const float* x, const float* w, const float* b, i
 
 int launch_groupnorm_stats(const float* x, const RowSpace& rs, int dim, double* stats,
                            cudaStream_t stream) {
-    return launch_gn_dispatch(dim, kPrecBf16, x, rs, nullptr, nullptr, nullptr, 0.f, nullptr, stream, nullptr, true,
-                              stats);
+    return launch_gn_dispatch(dim, kPrecBf16, x, rs, nullptr, nullptr, nullptr, 0.f, nullptr, stream, true, stats);
 }
 
 int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, int dim,
                                  const double* stats, const float* gamma, const float* beta,
-                                 float eps, void* out, cudaStream_t stream, float2* mean_rstd) {
-    return launch_gn_dispatch(dim, prec, x, rs, stats, gamma, beta, eps, out, stream, mean_rstd, false, nullptr);
+                                 float eps, void* out, cudaStream_t stream) {
+    return launch_gn_dispatch(dim, prec, x, rs, stats, gamma, beta, eps, out, stream, false, nullptr);
 }
 
 }  // namespace b200
