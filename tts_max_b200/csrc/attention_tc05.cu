@@ -8,14 +8,19 @@
 // 256 TMEM columns each) so one CTA's softmax (MUFU-bound: 128x128 exponentials per tile) overlaps
 // the other's MMAs.
 //
-//   thread 0         control duties, interleaved with its own softmax row at the points where it would
-//                    wait anyway: TMA loads (Q once; K,V tiles of 128 keys, 2-stage ring) and
+//   warp 8 (lane 0)  control: TMA loads (Q once; K,V tiles of 128 keys, 2-stage ring) and
 //                    tcgen05.mma issue:  S = Q K^T   (M128 N128 K64,  A,B K-major from smem)
 //                                        O_j = P V   (M128 N64  K128, A = P from TENSOR MEMORY,
 //                                                     B = V MN-major straight from its TMA tile)
-//   all 256 threads  two threads per query row (= TMEM lane), 64 keys each: tcgen05.ld S, online
+//                    A tcgen05.mma costs ~60 ns to issue (tools/attn_trace.cu): 12 per tile. With
+//                    the issuing thread inside a softmax warp that was 0.8 of a 2.25 us tile on the
+//                    critical path (its warp stalled, the other seven waited at the P barrier); a
+//                    warp of its own issues S_{j+1} first and P V_j while the softmax of tile j+1 runs.
+//   warps 0-7        two threads per query row (= TMEM lane), 64 keys each: tcgen05.ld S, online
 //                    softmax in fp32 (one smem exchange of the row max per tile), P -> bf16/fp16 -> tcgen05.st into TMEM, fold
 //                    the per-tile O_j from TMEM into register accumulators with the max correction.
+// Tried and measured slower: half of the exponentials as a degree-3 polynomial on the FMA pipe
+// (the softmax phase is as issue-bound as it is MUFU-bound: c2 55.5 -> 58.3 us, c4 306 -> 344 us).
 // TMEM -> register bandwidth is the scarce resource (ncu: identical time for very different softmax
 // instruction counts): S is read once per tile, O is accumulated by the tensor core in TMEM and a
 // row rescales its accumulator (tcgen05.ld / st) only when its running max actually changes.
@@ -29,12 +34,28 @@ namespace b200 {
 int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows);
 
+// in-kernel timeline for tools/attn_trace.cu; compiles to nothing in the product build
+#ifdef B200_ATTN_TRACE
+__device__ unsigned long long* g_attn_trace = nullptr;  // [CTAs][64] globaltimer stamps of thread 0 (softmax) / 256 (control)
+#define ATTN_TRACE(slot)                                                                          \
+    do {                                                                                          \
+        if ((threadIdx.x == 0 || threadIdx.x == 256) && g_attn_trace != nullptr) {                \
+            unsigned long long t_;                                                                \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+            g_attn_trace[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = t_; \
+        }                                                                                         \
+    } while (0)
+#else
+#define ATTN_TRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kD = 64;            // head dim
 constexpr int kBQ = 128;          // queries per CTA
 constexpr int kBK = 128;          // keys per tile
-constexpr int kThreads = 256;     // two threads per query row; thread 0 also issues TMA / MMA
+constexpr int kSoftmaxThreads = 256;  // two threads per query row
+constexpr int kThreads = kSoftmaxThreads + 32;  // + the control warp (TMA / MMA issue)
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 halfs
 constexpr uint32_t kTmemCols = 256;    // S: 128 columns, O_j: 64, P (16-bit pairs): 64
 
@@ -82,11 +103,13 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     float* red = reinterpret_cast<float*>(smem + AttnSmem::kRed);  // [2 parities][2 halves][128 rows]
 
     pdl_launch_dependents();
+    ATTN_TRACE(0);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int half = warp >> 2;               // which 64 keys of a tile / which 32 output columns
     const int r = (warp & 3) * 32 + lane;     // query row == TMEM lane
-    const bool ctrl = threadIdx.x == 0;       // also a softmax thread; see the header comment
+    const bool ctrl_warp = warp == 8;         // control warp; warps 0-7 are softmax warps
+    const bool ctrl = ctrl_warp && lane == 0;
     const int4 wk = work[blockIdx.x];
     const int row0 = wk.x, T_utt = wk.y, q0 = wk.z;
     const int head = blockIdx.y;
@@ -99,16 +122,17 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         mbar_init(&bar_kv_full[0], 1);
         mbar_init(&bar_kv_full[1], 1);
         mbar_init(bar_s_full, 1);
-        mbar_init(bar_p_full, kThreads);
+        mbar_init(bar_p_full, kSoftmaxThreads);
         mbar_init(bar_o_full, 1);
         fence_barrier_init();
     }
     __syncwarp();
-    if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+    if (ctrl_warp) tmem_alloc<kTmemCols>(tmem_slot);
     tc05_fence_before();
     __syncthreads();
     tc05_fence_after();
     pdl_wait();  // prologue above overlaps the predecessor's tail; no global access before this point
+    ATTN_TRACE(1);
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tmem_s = tmem_base + lane_addr + half * 64;        // this thread's 64 score columns
@@ -135,18 +159,46 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
             umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0);
         umma_commit(bar_s_full);
     };
-    if (ctrl) {
-        mbar_arrive_expect_tx(bar_q, kTileBytes);
-        tma_load_2d(sQ, &tmap_qkv, bar_q, head * kD, row0 + q0);
-        load_kv(0);
-        if (n_kv > 1) load_kv(1);
-        mbar_wait(bar_q, 0);
-        mbar_wait(&bar_kv_full[0], 0);
-        tc05_fence_after();
-        issue_s(0);
-    }
-    __syncwarp();
-
+    if (ctrl_warp) {
+        if (ctrl) {
+            mbar_arrive_expect_tx(bar_q, kTileBytes);
+            tma_load_2d(sQ, &tmap_qkv, bar_q, head * kD, row0 + q0);
+            load_kv(0);
+            if (n_kv > 1) load_kv(1);
+            mbar_wait(bar_q, 0);
+            mbar_wait(&bar_kv_full[0], 0);
+            tc05_fence_after();
+            ATTN_TRACE(2);
+            issue_s(0);
+            for (int j = 0; j < n_kv; ++j) {
+                // every row's P_j is in TMEM, S_j has been read and O rescaled: next S first (the
+                // softmax warps are waiting for it), then O += P_j V_j behind it
+                mbar_wait(bar_p_full, j & 1);
+                tc05_fence_after();
+                if (j < 6) ATTN_TRACE(8 + j * 8 + 5);  // every row's P_j stored
+                if (j + 1 < n_kv) {
+                    mbar_wait(&bar_kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    tc05_fence_after();
+                    issue_s(j + 1);
+                }
+                const uint32_t v_base = smem_u32(sV + (j & 1) * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    // P from TMEM (16 keys = 8 columns per step); V MN-major (16 rows of 128 B per step)
+                    const uint64_t b_desc = umma_desc_mn_sw128(v_base + k * 16 * 128);
+                    umma_f16_ts(tmem_base + 128, tmem_base + 192 + k * 8, b_desc, idesc_o, (j | k) != 0);
+                }
+                umma_commit(bar_o_full);
+                if (j < 6) ATTN_TRACE(8 + j * 8 + 6);  // S_{j+1} and P V_j issued
+                if (j + 2 < n_kv) {
+                    // K/V stage j & 1 is free once P V_j has retired: refill it with tile j + 2
+                    mbar_wait(bar_o_full, j & 1);
+                    load_kv(j + 2);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
     // ---------------- softmax: two threads per query row, 64 keys each ----------------
     // TMEM -> register bandwidth (~64 B/clk/SM) is the scarce resource: S is read exactly once per
     // tile and kept in registers, and O is accumulated by the tensor core inside TMEM; a row only
@@ -159,10 +211,12 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         const bool full = n_valid >= 64;
         mbar_wait(bar_s_full, j & 1);
         tc05_fence_after();
+        if (j < 6) ATTN_TRACE(8 + j * 8 + 0);  // S_j ready
         uint32_t sr[64];
         tmem_ld_32x32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
         tmem_ld_32x32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
         tmem_ld_wait();
+        if (j < 6) ATTN_TRACE(8 + j * 8 + 1);  // S_j in registers
         if (!full) {
 #pragma unroll
             for (int i = 0; i < 64; ++i)
@@ -179,6 +233,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         // only the two warps that share this lane quarter exchange data: 4 independent 64-thread
         // named barriers instead of one CTA-wide barrier per tile
         asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+        if (j < 6) ATTN_TRACE(8 + j * 8 + 2);  // row max exchanged
         const float m_new = fmaxf(m_run, fmaxf(red_j[r], red_j[128 + r]));
         const float corr = ex2_approx((m_run - m_new) * c);  // first tile: ex2(-inf) = 0
         const float m_scaled = m_new * c;
@@ -186,26 +241,30 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
             // P V_{j-1} retired: P, its K/V stage and the O accumulator are quiescent
             mbar_wait(bar_o_full, (j - 1) & 1);
             tc05_fence_after();
-            if (ctrl && j + 1 < n_kv) load_kv(j + 1);  // stage (j+1)&1 was tile j-1's: free now
             // tcgen05.ld/st are .sync.aligned: the decision must be warp-uniform, so a warp rescales
             // when ANY of its 32 rows moved its max (the others multiply by exactly 1)
             if (__any_sync(0xffffffffu, corr != 1.f)) {
-                uint32_t orr[32];
-                tmem_ld_32x32(tmem_o, orr);
-                tmem_ld_wait();
+                // two 16-column halves: only 16 registers live next to the 64 scores (2 CTAs per SM
+                // leave 96 registers per thread)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * corr);
-                tmem_st_32x16(tmem_o, *reinterpret_cast<uint32_t(*)[16]>(&orr[0]));
-                tmem_st_32x16(tmem_o + 16, *reinterpret_cast<uint32_t(*)[16]>(&orr[16]));
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t orr[16];
+                    tmem_ld_32x16(tmem_o + hf * 16, orr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * corr);
+                    tmem_st_32x16(tmem_o + hf * 16, orr);
+                }
             }
         }
+        if (j < 6) ATTN_TRACE(8 + j * 8 + 3);  // P V_{j-1} retired, O rescaled
         l_run *= corr;
         m_run = m_new;
         // P = exp2(s * c - m * c) -> 16-bit pairs -> TMEM (A operand of P V)
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            uint32_t pk[16];
+            uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float p0 = ex2_approx(fmaf(__uint_as_float(sr[ch * 16 + 2 * i]), c, -m_scaled));
@@ -213,8 +272,6 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
                 if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
                 pk[i] = Half16<T>::pack(p0, p1);
             }
-#pragma unroll
-            for (int i = 8; i < 16; ++i) pk[i] = 0;
             // 16 keys -> 8 packed columns of this row's lane
             asm volatile(
                 "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
@@ -226,29 +283,12 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         tmem_st_wait();
         tc05_fence_before();
         mbar_arrive(bar_p_full);
-        if (ctrl) {
-            // every row's P_j is in TMEM, S_j has been read and O rescaled: next S, then O += P_j V_j
-            mbar_wait(bar_p_full, j & 1);
-            tc05_fence_after();
-            if (j + 1 < n_kv) {
-                mbar_wait(&bar_kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                tc05_fence_after();
-                issue_s(j + 1);
-            }
-            const uint32_t v_base = smem_u32(sV + (j & 1) * kTileBytes);
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-                // P from TMEM (16 keys = 8 columns per step); V MN-major (16 rows of 128 B per step)
-                const uint64_t b_desc = umma_desc_mn_sw128(v_base + k * 16 * 128);
-                umma_f16_ts(tmem_base + 128, tmem_base + 192 + k * 8, b_desc, idesc_o, (j | k) != 0);
-            }
-            umma_commit(bar_o_full);
-        }
-        __syncwarp();
+        if (j < 6) ATTN_TRACE(8 + j * 8 + 4);  // own P_j stored
     }
     // the finished accumulator and the two halves of the row sum
     mbar_wait(bar_o_full, (n_kv - 1) & 1);
     tc05_fence_after();
+    ATTN_TRACE(3);  // last P V retired
     uint32_t orr[32];
     tmem_ld_32x32(tmem_o, orr);
     tmem_ld_wait();
@@ -269,10 +309,13 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         }
     }
 
+    }  // softmax warps
+    ATTN_TRACE(4);  // output stored
     tc05_fence_before();
     __syncthreads();
     tc05_fence_after();
-    if (warp == 0) tmem_dealloc<kTmemCols>(tmem_base);
+    if (ctrl_warp) tmem_dealloc<kTmemCols>(tmem_base);
+    ATTN_TRACE(5);
 }
 
 }  // namespace
