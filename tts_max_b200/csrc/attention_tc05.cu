@@ -21,6 +21,10 @@
 //                    the per-tile O_j from TMEM into register accumulators with the max correction.
 // Tried and measured slower: half of the exponentials as a degree-3 polynomial on the FMA pipe
 // (the softmax phase is as issue-bound as it is MUFU-bound: c2 55.5 -> 58.3 us, c4 306 -> 344 us).
+// Tried and measured equal: persistent CTAs (2 per SM walking the item list on one global tile
+// counter, the control warp prefetching the next item's Q/K/V): 6 % faster alone on c2, nothing on
+// c4, and 0.5-1 % SLOWER inside the decode step, where short-lived CTAs let the next GEMM's CTAs
+// (programmatic dependent launch) start on SMs as they drain.
 // TMEM -> register bandwidth is the scarce resource (ncu: identical time for very different softmax
 // instruction counts): S is read once per tile, O is accumulated by the tensor core in TMEM and a
 // row rescales its accumulator (tcgen05.ld / st) only when its running max actually changes.
