@@ -208,8 +208,9 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
     const int r_hi = min(r_lo + slab, rows);
     int cur_u = -1;
     float2 mr = make_float2(0.f, 0.f);
-    for (int r = r_lo + sub; r < r_hi; r += kRows) {
-        const int u = row_utt[r];
+    // two rows per step with all four 128-bit loads issued before anything depends on them (the
+    // pass is HBM-bound: bytes in flight per thread are what it needs)
+    auto finish_row = [&](int r, int u, const float4& v0, const float4& v1) {
         uint4 packed = make_uint4(0u, 0u, 0u, 0u);
         if (u >= 0) {
             if (u != cur_u) {
@@ -220,8 +221,6 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
                 var = var < 0.0 ? 0.0 : var;
                 mr = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
             }
-            const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * DIM + c0);
-            const float4 v0 = xp[0], v1 = xp[1];
             float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -234,6 +233,17 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
             packed.w = Half16<OutT>::pack(y[6], y[7]);
         }
         *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * DIM + c0) = packed;
+    };
+    for (int r = r_lo + sub; r < r_hi; r += 2 * kRows) {
+        const int r2 = r + kRows;
+        const bool has2 = r2 < r_hi;
+        const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * DIM + c0);
+        const float4* xq = reinterpret_cast<const float4*>(x + static_cast<size_t>(has2 ? r2 : r) * DIM + c0);
+        const float4 a0 = xp[0], a1 = xp[1], b0 = xq[0], b1 = xq[1];
+        const int u1 = row_utt[r];
+        const int u2 = has2 ? row_utt[r2] : -1;
+        finish_row(r, u1, a0, a1);
+        if (has2) finish_row(r2, u2, b0, b1);
     }
 }
 
@@ -251,8 +261,10 @@ int launch_gn_typed(int prec, const float* x, const RowSpace& rs, const double* 
     }
     if (rs.rows <= 0) return 0;
     constexpr int kRows = kGnThreads / (DIM / 8);
+    // one wave of 4 CTAs per SM (64 registers): a CTA's slab is long enough to amortise its
+    // gamma / beta / statistics prologue (ncu: 1184 short CTAs ran as two half-empty waves)
     int grid = (rs.rows + kRows - 1) / kRows;
-    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
     if (prec == kPrecBf16)
         B200_CUDA_OK(launch_kernel(groupnorm_apply_swish_kernel<__nv_bfloat16, DIM>, dim3(grid), dim3(kGnThreads), 0,
                                    stream, x, rs.row_utt, rs.rows, stats, rs.utt_len, eps, gamma,
