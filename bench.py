@@ -48,7 +48,8 @@ LINEAR_FLOPS_PER_TOKEN = 373_854_208  # SURVEY.md 8a / BASELINE.md 4
 # project_out, fc_post_a and the embed conv are folded into one lookup at load time: their
 # 4 194 304 + 14 680 064 FLOP/token of the reference's algorithmic work are not executed and not counted
 FOLDED_FLOPS_PER_TOKEN = 4_194_304 + 14_680_064
-GEMM_FLOPS_PER_TOKEN = 50_331_648 + 301_989_888 + 2_625_536  # tcgen05 GEMM/conv kernel
+FRONTEND_GEMM_FLOPS_PER_TOKEN = 2 * 128 * 1024  # what is executed instead: codes im2col x [hi | lo] coefficients
+GEMM_FLOPS_PER_TOKEN = FRONTEND_GEMM_FLOPS_PER_TOKEN + 50_331_648 + 301_989_888 + 2_625_536  # tcgen05 GEMM/conv kernel
 ATTN_FLOPS_PER_TOKEN_PER_T = 49_152
 
 
@@ -357,11 +358,11 @@ def run_ours(args):
         dec.profile(False)
         peaks = read_peaks()
         gemm_ms = sum(v for k, v in stage_ms.items() if k.endswith("_gemm"))
-        n_gemm = 8 + 12 * 4 + 1  # 8 conv3, 48 transformer linears, head
+        n_gemm = 1 + 8 + 12 * 4 + 1  # folded front end (K = 128), 8 conv3, 48 transformer linears, head
         gemm_flops = GEMM_FLOPS_PER_TOKEN * total_tokens
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["tflops_sustained"]
-        step_flops = (LINEAR_FLOPS_PER_TOKEN - FOLDED_FLOPS_PER_TOKEN + ATTN_FLOPS_PER_TOKEN_PER_T * tokens) * total_tokens
+        step_flops = (LINEAR_FLOPS_PER_TOKEN - FOLDED_FLOPS_PER_TOKEN + FRONTEND_GEMM_FLOPS_PER_TOKEN + ATTN_FLOPS_PER_TOKEN_PER_T * tokens) * total_tokens
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")
         if os.path.exists(tpath) and args.workload == "c2":
@@ -389,7 +390,7 @@ def run_ours(args):
                     "frac": round(gbs / hbm, 4), "ms_per_step": round(ms, 4), "launches_per_step": launches}
 
         roofline["hbm_kernels"] = [
-            hbm_entry("fsq_frontend_kernel (project_out o fc_post_a o embed conv7 folded: 8 B id in, 1024 x 4 B out)", "fsq_lookup", 8 + 4096, 1),
+            hbm_entry("fsq_im2col_kernel (ids -> codes of 7 neighbouring frames: 8 B id in, 128 x 2 B out)", "fsq_lookup", 8 + 256, 1),
             # 8 apply passes (4096 B in, 2048 B out) + 1 stand-alone statistics pass (4096 B in); the other
             # seven GroupNorms get their statistics from the producing GEMM's epilogue
             hbm_entry("groupnorm_apply_swish x8 + groupnorm_stats x1 (per apply: 4096 B in, 2048 B out)", "groupnorm_swish",

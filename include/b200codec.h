@@ -131,11 +131,13 @@ int b200codec_take_id_error(B200Codec* h);
  * flash kernel it replaced (kept for A/B measurements and as a second opinion in the tests). */
 int b200codec_set_attention_impl(int impl);
 
-/* Front-end fold (default on): project_out, fc_post_a and the backbone's embed conv (k = 7) are linear
- * maps back to back, so ids -> embed output runs as ONE 7-tap x 8-digit lookup whose coefficients are
- * folded in fp64 at load time. Off = 8 -> 1024 lookup (project_out o fc_post_a) followed by the conv7
- * GEMM on 16-bit operands. A/B switch; both agree with the fp32 reference, the fold more closely. */
-int b200codec_set_frontend_fold(int on);
+/* Front end (ids -> embed output). project_out, fc_post_a and the backbone's embed conv (k = 7) are
+ * linear maps back to back, so the conv output is a linear function of the 7 neighbouring codes whose
+ * coefficients are folded in fp64 at load time. mode 1 (default): im2col of the codes (exact in 16 bits)
+ * + one K = 128 tensor-core GEMM against the coefficients split hi + lo; mode 2: the same fold as an fp32
+ * FMA lookup kernel; mode 0: 8 -> 1024 lookup (project_out o fc_post_a) + conv7 GEMM on 16-bit operands.
+ * A/B switch; all agree with the fp32 reference, the folds more closely. */
+int b200codec_set_frontend_fold(int mode);
 
 /* decode_host with a PINNED output buffer lets the last kernel store the PCM straight into host
  * memory (default on; pageable buffers always take the staged device buffer + copy). A/B switch. */

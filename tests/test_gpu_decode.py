@@ -56,8 +56,9 @@ def test_batched_forward_vs_reference_golden(gpu_decoders, golden, prec):
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 def test_frontend_fold_equals_lookup_plus_conv7(gpu_decoders, golden, prec):
-    """ids -> embed output as one folded 7-tap lookup (default) vs lookup + conv7 GEMM: the same
-    function, both within tolerance of the reference, the fp64-folded one at least as close; edge
+    """ids -> embed output: the folded forms (mode 1: im2col + K = 128 tensor-core GEMM with hi/lo
+    coefficients, the default; mode 2: fp32 FMA lookup) against lookup + conv7 GEMM (mode 0): the same
+    function, all within tolerance of the reference, the fp64-folded ones at least as close; edge
     frames (utterances of 1..7 tokens, where taps fall off the ends) included."""
     from tts_max_b200 import _lib
 
@@ -68,19 +69,23 @@ def test_frontend_fold_equals_lookup_plus_conv7(gpu_decoders, golden, prec):
     g = torch.Generator().manual_seed(321)
     lens = [1, 2, 3, 4, 5, 6, 7, 40]
     short = torch.randint(0, 65536, (sum(lens),), generator=g)
+    wav, shorts = {}, {}
     try:
-        _lib.check(lib.b200codec_set_frontend_fold(0))
-        gemm_wav = d(ids)[0, 0].cpu()
-        gemm_short = d.decode_packed_host(short, lens).clone()
-        _lib.check(lib.b200codec_set_frontend_fold(1))
-        fold_wav = d(ids)[0, 0].cpu()
-        fold_short = d.decode_packed_host(short, lens).clone()
+        for mode in (0, 2, 1):
+            _lib.check(lib.b200codec_set_frontend_fold(mode))
+            wav[mode] = d(ids)[0, 0].cpu()
+            shorts[mode] = d.decode_packed_host(short, lens).clone()
     finally:
         _lib.check(lib.b200codec_set_frontend_fold(1))
-    check_wave(ref, gemm_wav, prec, "u37 lookup+conv7")
-    check_wave(ref, fold_wav, prec, "u37 folded front end")
-    assert O.snr_db(ref, fold_wav) >= O.snr_db(ref, gemm_wav) - 0.5
-    check_wave(gemm_short, fold_short, prec, "short utterances, folded vs lookup+conv7")
+    for mode, what in ((0, "lookup+conv7"), (2, "folded fp32 FMA"), (1, "folded tensor-core")):
+        check_wave(ref, wav[mode], prec, f"u37 {what}")
+    assert O.snr_db(ref, wav[1]) >= O.snr_db(ref, wav[0]) - 0.5
+    assert O.snr_db(ref, wav[2]) >= O.snr_db(ref, wav[0]) - 0.5
+    # the two folds differ only by the hi/lo split of the coefficients (~2^-17) and summation order
+    check_wave(shorts[2], shorts[1], prec, "short utterances, tensor-core vs FMA fold")
+    check_wave(shorts[0], shorts[1], prec, "short utterances, folded vs lookup+conv7")
+    with pytest.raises(_lib.B200CodecError):
+        _lib.check(lib.b200codec_set_frontend_fold(3))
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])

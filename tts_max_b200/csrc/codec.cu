@@ -25,7 +25,9 @@
 namespace b200 {
 
 int g_use_pdl = 1;
-static int g_frontend_fold = 1;  // ids -> embed output as one folded lookup (0: lookup + conv7 GEMM)
+// ids -> embed output: 1 = folded, im2col of the codes + one K = 128 tensor-core GEMM (default);
+// 2 = folded, fp32 FMA lookup kernel; 0 = 8 -> 1024 lookup + conv7 GEMM on 16-bit operands
+static int g_frontend_fold = 1;
 static int g_zero_copy_out = 1;  // decode_host: write PCM directly into pinned host memory
 
 static thread_local char g_err[1024] = {0};
@@ -139,7 +141,8 @@ struct B200Codec {
     float* w_pre = nullptr;  // fc_post_a o project_out folded: [C, 8] codebook projection ...
     float* b_pre = nullptr;  // ... and [C] bias (fp32)
     float* m_fold = nullptr;   // embed o fc_post_a o project_out: [7][C][8] ...
-    float* cb_fold = nullptr;  // ... and the per-tap bias part [7][C]
+    float* cb_fold = nullptr;  // ... and the per-tap bias part [7][C] (fp32 FMA form, A/B path 2)
+    void* w_front = nullptr;   // the same coefficients as a GEMM operand [C][128] = [hi | lo], operand dtype
     float2* twiddle = nullptr;
     float *rope_cos = nullptr, *rope_sin = nullptr;
 
@@ -752,11 +755,30 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
     const int C = h->C, prec = h->cfg.precision;
     const RowSpace& rs = h->rs;
     B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * h->gn_slots * rs.n_utts * 64, s));
-    if (g_frontend_fold) {
-        // project_out (8 -> 2048, decoder.py:77), fc_post_a (2048 -> 1024, decoder.py:79) and the
-        // backbone's embed Conv1d (k = 7, decoder_modules.py:340,392) are linear maps back to back:
-        // the conv output is a 7-tap x 8-digit lookup with coefficients folded in fp64 at load time
-        // (see fsq_frontend_kernel). No 2048-wide intermediate, no K = 2048 / K = 7168 GEMM.
+    // GroupNorm statistics slot k (k = 2 * block + {0: norm1, 1: norm2}) of utterance u, group g:
+    // gn_stats[((k * n_utts + u) * 32 + g) * 2 + {sum, sumsq}]
+    const bool gn_fused = gn_stats_in_gemm(rs.rows, C);
+    auto gn_slot = [&](int k) { return gn_fused ? h->gn_stats + static_cast<size_t>(k) * rs.n_utts * 64 : nullptr; };
+    bool gn0_done = false;  // prior_net.0's first GroupNorm statistics already reduced
+    // project_out (8 -> 2048, decoder.py:77), fc_post_a (2048 -> 1024, decoder.py:79) and the backbone's
+    // embed Conv1d (k = 7, decoder_modules.py:340,392) are linear maps back to back: the conv output is
+    // a linear function of the seven neighbouring codes, with coefficients folded in fp64 at load time.
+    // No 2048-wide intermediate, no K = 2048 / K = 7168 GEMM.
+    if (g_frontend_fold == 1) {
+        {
+            Stage t(h, "fsq_lookup", s);
+            RUN(launch_fsq_im2col(ids_dev, id_type, rs.row_tok, rs.rows, prec, h->xc, h->err_flag_dev, s));
+        }
+        {
+            // x = A [hi | lo]^T on the tensor cores (K = 128); the epilogue also reduces the first
+            // GroupNorm's statistics
+            Stage t(h, "frontend_gemm", s);
+            NormFuse nf0;
+            nf0.gn_stats = gn_slot(0);
+            gn0_done = gn_fused;
+            RUN(gemm(h, h->xc, 128, h->w_front, C, 1, h->x, true, C, C, nullptr, nullptr, kActNone, false, s, nf0));
+        }
+    } else if (g_frontend_fold == 2) {
         Stage t(h, "fsq_lookup", s);
         RUN(launch_fsq_frontend(ids_dev, id_type, rs.row_tok, rs.rows, h->m_fold, h->cb_fold,
                                 h->m("decoder.backbone.embed.bias"), C, h->x, h->err_flag_dev, s));
@@ -785,11 +807,7 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
         produce.ss_out = h->ss;
         consume.ss_in = h->ss;
     }
-    // GroupNorm statistics slot k (k = 2 * block + {0: norm1, 1: norm2}) of utterance u, group g:
-    // gn_stats[((k * n_utts + u) * 32 + g) * 2 + {sum, sumsq}]
-    const bool gn_fused = gn_stats_in_gemm(rs.rows, C);
-    auto gn_slot = [&](int k) { return gn_fused ? h->gn_stats + static_cast<size_t>(k) * rs.n_utts * 64 : nullptr; };
-    if (resnet_block(h, h->res[0], 0, s, NormFuse(), false, gn_slot(2))) return 1;
+    if (resnet_block(h, h->res[0], 0, s, NormFuse(), gn0_done, gn_slot(2))) return 1;
     if (resnet_block(h, h->res[1], 2, s, produce, gn_fused, nullptr)) return 1;
     for (int l = 0; l < h->L; ++l) {
         const LayerW& w = h->layers[l];
@@ -1106,7 +1124,7 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     const int C = h->C, V = h->V, L = h->L, prec = h->cfg.precision;
     const size_t es = operand_bytes(prec);
     const size_t n_head = static_cast<size_t>(h->n_fft + 2) * C;
-    size_t elems = static_cast<size_t>(C) * C * 7 +
+    size_t elems = static_cast<size_t>(C) * 128 + static_cast<size_t>(C) * C * 7 +
                    8 * static_cast<size_t>(C) * C * 3 +
                    static_cast<size_t>(L) * (3ull * C * C + 1ull * C * C + 8ull * C * C) + n_head;
     for (int i = 0; i < h->n_up; ++i) {
@@ -1191,6 +1209,37 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
                     mf[(static_cast<size_t>(t) * C + c) * 8 + d] = static_cast<float>(acc[t][d]);
                 cbf[static_cast<size_t>(t) * C + c] = static_cast<float>(acc[t][8]);
             }
+        }
+        {
+            // GEMM form: B[c][8 * tap + d] = M, B[c][56 + tap] = cb, B[c][63] = embed bias; columns
+            // 64..127 hold the part the 16-bit rounding of columns 0..63 lost (hi + lo ~ fp32)
+            std::vector<float> be(C);
+            B200_CUDA_OK(cudaMemcpy(be.data(), h->m("decoder.backbone.embed.bias"), be.size() * 4,
+                                    cudaMemcpyDeviceToHost));
+            std::vector<uint16_t> wf(static_cast<size_t>(C) * 128);
+            auto split = [&](float v, uint16_t& hi, uint16_t& lo) {
+                if (prec == kPrecBf16) {
+                    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+                    const __nv_bfloat16 b = __float2bfloat16_rn(v - __bfloat162float(a));
+                    hi = *reinterpret_cast<const uint16_t*>(&a);
+                    lo = *reinterpret_cast<const uint16_t*>(&b);
+                } else {
+                    const __half a = __float2half_rn(v);
+                    const __half b = __float2half_rn(v - __half2float(a));
+                    hi = *reinterpret_cast<const uint16_t*>(&a);
+                    lo = *reinterpret_cast<const uint16_t*>(&b);
+                }
+            };
+            for (int c = 0; c < C; ++c)
+                for (int col = 0; col < 64; ++col) {
+                    float v;
+                    if (col < 56) v = mf[(static_cast<size_t>(col >> 3) * C + c) * 8 + (col & 7)];
+                    else if (col < 63) v = cbf[static_cast<size_t>(col - 56) * C + c];
+                    else v = be[c];
+                    split(v, wf[static_cast<size_t>(c) * 128 + col], wf[static_cast<size_t>(c) * 128 + 64 + col]);
+                }
+            h->w_front = take(static_cast<size_t>(C) * 128);
+            B200_CUDA_OK(cudaMemcpy(h->w_front, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
         }
         if (!h->m_fold) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->m_fold), mf.size() * 4));
         if (!h->cb_fold) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->cb_fold), cbf.size() * 4));
@@ -1390,8 +1439,10 @@ int b200codec_set_attention_impl(int impl) {
     return 0;
 }
 
-int b200codec_set_frontend_fold(int on) {
-    g_frontend_fold = on != 0;
+int b200codec_set_frontend_fold(int mode) {
+    B200_CHECK(mode >= 0 && mode <= 2, "front-end mode must be 0 (lookup + conv7 GEMM), 1 (folded, tensor cores) "
+                                       "or 2 (folded, fp32 FMA kernel)");
+    g_frontend_fold = mode;
     return 0;
 }
 

@@ -222,6 +222,64 @@ fsq_frontend_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row
 }
 
 // ---------------------------------------------------------------------------
+// The same folded front end as a GEMM: ids -> A [rows, 128] (operand dtype), the im2col of the seven
+// neighbouring codes. Column 8 * tap + d = digit d of frame t + tap - 3 (0 when that frame does not
+// exist), 56 + tap = "frame exists", 63 = 1; columns 64..127 repeat 0..63. Every value is 0, +-0.5
+// or +-1, exact in bf16 and fp16, so x = A B^T with B = [hi(coef) | lo(coef)] (the folded
+// coefficients split into two 16-bit parts, launch_fsq_frontend_gemm's caller) reproduces the fp32
+// fold to ~2^-17 on the tensor cores, and the GroupNorm statistics of x ride the GEMM epilogue.
+// One warp per row: lane l writes columns 4l .. 4l+3 (8 bytes), 256 bytes per row.
+template <typename OutT, typename IdT>
+__global__ void __launch_bounds__(256)
+fsq_im2col_kernel(const IdT* __restrict__ ids, const int32_t* __restrict__ row_tok, int rows,
+                  OutT* __restrict__ a, int* __restrict__ err_flag) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int col = (lane & 15) * 4;            // 0..60; lanes 16-31 write the copy at +64
+    const int tap = col < 56 ? col >> 3 : 3;    // flag columns are handled below
+    auto frame_id = [&](int rr, bool& valid) -> unsigned {
+        valid = false;
+        if (rr < 0 || rr >= rows) return 0u;
+        const int tok = row_tok ? row_tok[rr] : rr;
+        if (tok < 0) return 0u;
+        const long long id = static_cast<long long>(ids[tok]);
+        if ((id < 0 || id > 65535) && lane == 0) atomicExch(err_flag, 1);
+        valid = true;
+        return static_cast<unsigned>(id) & 0xFFFFu;
+    };
+    bool centre;
+    (void)frame_id(r, centre);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (centre) {  // halo rows stay all-zero: their x row is zero
+        if (col < 56) {
+            bool ok;
+            const unsigned uid = frame_id(r + tap - 3, ok);
+            const int d0 = col & 7;  // 0 or 4
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                v[i] = ok ? static_cast<float>(static_cast<int>((uid >> (2 * (d0 + i))) & 3) - 2) * 0.5f : 0.f;
+        } else {
+            // columns 56..63: "frame exists" of taps 0..6, then the constant 1
+            const int t0 = col - 56;  // 0 or 4
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i;
+                bool ok = true;
+                if (t < 7) (void)frame_id(r + t - 3, ok);
+                v[i] = ok ? 1.f : 0.f;
+            }
+        }
+    }
+    uint2 w;
+    w.x = Half16<OutT>::pack(v[0], v[1]);
+    w.y = Half16<OutT>::pack(v[2], v[3]);
+    *reinterpret_cast<uint2*>(a + static_cast<size_t>(r) * 128 + lane * 4) = w;
+}
+
+// ---------------------------------------------------------------------------
 // FSQ quantise (encode direction): the mirror image of the lookup above.
 //
 // Replaces vector_quantize_pytorch.ResidualFSQ.forward as called by Encoder.quantize
@@ -357,6 +415,27 @@ int launch_fsq_frontend(const void* ids, int id_type, const int32_t* row_tok, in
         B200_CUDA_OK(launch_kernel(fsq_frontend_kernel<int>, grid, dim3(kFrontThreads), 0, stream,
                                    static_cast<const int*>(ids), row_tok, rows, m_fold, cb_fold, b_embed, C, x,
                                    err_flag));
+    return 0;
+}
+
+int launch_fsq_im2col(const void* ids, int id_type, const int32_t* row_tok, int rows, int prec, void* a,
+                      int* err_flag, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    const dim3 grid((rows + 7) / 8), block(256);
+#define B200_IM2COL(OUT, ID)                                                                               \
+    B200_CUDA_OK(launch_kernel(fsq_im2col_kernel<OUT, ID>, grid, block, 0, stream, static_cast<const ID*>(ids), \
+                               row_tok, rows, static_cast<OUT*>(a), err_flag))
+    if (prec == kPrecBf16) {
+        if (id_type == 1) B200_IM2COL(__nv_bfloat16, long long);
+        else B200_IM2COL(__nv_bfloat16, int);
+    } else if (prec == kPrecFp16) {
+        if (id_type == 1) B200_IM2COL(__half, long long);
+        else B200_IM2COL(__half, int);
+    } else {
+        set_error("fsq im2col: unsupported precision %d", prec);
+        return 1;
+    }
+#undef B200_IM2COL
     return 0;
 }
 

@@ -49,6 +49,10 @@ int launch_fsq_lookup(const void* ids, int id_type, const int32_t* row_tok, int 
 int launch_fsq_frontend(const void* ids, int id_type, const int32_t* row_tok, int rows, const float* m_fold,
                         const float* cb_fold, const float* b_embed, int C, float* x, int* err_flag,
                         cudaStream_t stream);
+// the folded front end as a GEMM operand: ids -> a [rows, 128] operand dtype (codes of the 7 neighbouring
+// frames, "frame exists" flags, constant 1; columns 64..127 repeat 0..63 for the hi/lo coefficient split)
+int launch_fsq_im2col(const void* ids, int id_type, const int32_t* row_tok, int rows, int prec, void* a,
+                      int* err_flag, cudaStream_t stream);
 // encode direction (encoder.py:73-78): features [n_tokens, ld] fp32 -> ids (id_type 0: int32, 1: int64);
 // z_out (optional) receives the eight projected values per token
 int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in, const float* b_in,
