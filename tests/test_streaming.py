@@ -1,0 +1,72 @@
+"""Stateful streaming decode: `StreamingDecoder.push` equals the defined semantics
+-- the reference forward on cat(context, new), trimmed to the new tokens' samples -- step by step,
+with and without the CUDA-graph replay; and the quality against the one-shot decode of the whole
+utterance is reported as a function of the context length."""
+
+import pytest
+import torch
+
+from oracle import codec_oracle as O
+
+
+def test_streaming_requires_cuda_decoder():
+    from tts_max_b200.codec import decoder, streaming
+
+    dec = decoder.Decoder(16000, 320, None, None, init_seed=0)   # stays on the CPU: no handle is created
+    with pytest.raises(RuntimeError):
+        streaming.StreamingDecoder(dec, n_streams=1)
+    with pytest.raises(ValueError):
+        streaming.StreamingDecoder(dec, n_streams=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_push_equals_window_decode(gpu_decoders, state_dict, use_graph):
+    from tts_max_b200.codec import streaming
+
+    d = gpu_decoders["bf16"]
+    n_streams, new, ctx_len, n_push = 3, 10, 20, 7
+    g = torch.Generator().manual_seed(17)
+    ids = torch.randint(0, 65536, (n_streams, new * n_push), generator=g)
+    sd = streaming.StreamingDecoder(d, n_streams, new_tokens=new, left_context=ctx_len, use_graph=use_graph)
+    for k in range(n_push):
+        out = sd.push(ids[:, k * new:(k + 1) * new])
+        assert out.shape == (n_streams, new * 320) and out.is_cuda
+        lo = max(0, (k + 1) * new - (ctx_len + new))
+        window = ids[:, lo:(k + 1) * new]
+        want = d(window.cuda())[:, 0, -new * 320:]
+        scale = max(1e-3, want.abs().max().item())
+        assert (out - want).abs().max().item() <= 1e-5 * scale, (k, use_graph)
+        assert sd.context_tokens == min(ctx_len, (k + 1) * new)
+        if k in (0, n_push - 1):   # pin the definition itself on the oracle: first and a steady-state step
+            ref = O.decoder_forward(state_dict, window[:1])[:, 0, -new * 320:]
+            assert O.snr_db(ref, out[:1].cpu()) >= 30.0
+    # a new stream after reset() sees no history
+    sd.reset()
+    first = sd.push(ids[:, :new])
+    want = d(ids[:, :new].cuda())[:, 0, :]
+    assert (first - want).abs().max().item() <= 1e-5 * max(1e-3, want.abs().max().item())
+    with pytest.raises(ValueError):
+        sd.push(ids[:, :new + 1])
+
+
+@pytest.mark.gpu
+def test_streaming_quality_vs_one_shot(gpu_decoders):
+    """Chunking changes GroupNorm / attention statistics, so streaming != one-shot by construction; more
+    context must not make it worse. (Random-init weights: the numbers characterise the method, not a
+    trained codec.)"""
+    from tts_max_b200.codec import streaming
+
+    d = gpu_decoders["bf16"]
+    ids = torch.randint(0, 65536, (2, 500), generator=torch.Generator().manual_seed(23))
+    full = d(ids.cuda())[:, 0, :]
+    snr = {}
+    for ctx_len in (0, 100, 450):
+        sd = streaming.StreamingDecoder(d, 2, new_tokens=50, left_context=ctx_len)
+        chunks = [sd.push(ids[:, k:k + 50]) for k in range(0, 500, 50)]
+        got = torch.cat(chunks, dim=1)
+        assert got.shape == full.shape and torch.isfinite(got).all()
+        snr[ctx_len] = O.snr_db(full.cpu(), got.cpu())
+    print(f"[streaming] SNR vs one-shot decode, 50-token chunks: {snr}")
+    assert snr[450] >= snr[100] - 1.0 and snr[100] >= snr[0] - 1.0
+    assert snr[450] >= 10.0     # 450 + 50 = the whole utterance from the last chunk on

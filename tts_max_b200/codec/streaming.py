@@ -1,0 +1,108 @@
+"""Stateful chunked decode for serving (BASELINE config 5's shape).
+
+The reference has no streaming decoder (`tools/serving/inference.py:155-170` is one-shot), and
+chunking changes what the model computes: GroupNorm statistics and the unmasked attention see the
+window, not the utterance. The semantics are therefore DEFINED as
+
+    audio(new tokens) = last `new * samples_per_token` samples of  Decoder.forward(cat(context, new))
+
+with `context` = the stream's previous `left_context` tokens (fewer at the start of a stream). That is
+exactly `batching.decode_stream_windows` on the window the stream has reached, so the parity oracle is
+the reference forward on the same window, trimmed -- and the quality against the one-shot decode of the
+whole utterance is a property of `left_context`, measured in tests/test_streaming.py.
+
+What this class adds is the state (per-stream token history on the device) and, once every stream has a
+full context, a FIXED window shape: the launch chain of one step is then captured once in a CUDA graph
+and replayed (tools/graph_ab.py: about 5 % at small sizes, identical samples).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from tts_max_b200.codec import decoder as decoder_lib
+
+
+class StreamingDecoder:
+    """`n_streams` independent streams advancing in lock step, `new_tokens` tokens per `push`."""
+
+    def __init__(self, decoder: decoder_lib.Decoder, n_streams: int, new_tokens: int = 50,
+                 left_context: int = 100, use_graph: bool = True):
+        if n_streams <= 0 or new_tokens <= 0 or left_context < 0:
+            raise ValueError("n_streams and new_tokens must be positive, left_context non-negative")
+        self._dec = decoder
+        self._device = decoder.device
+        if self._device.type != "cuda":
+            raise RuntimeError("StreamingDecoder needs a decoder on a CUDA device (there is no CPU path)")
+        self.n_streams = int(n_streams)
+        self.new_tokens = int(new_tokens)
+        self.left_context = int(left_context)
+        self.samples_per_token = decoder.samples_per_token
+        self._use_graph = bool(use_graph)
+        win = self.left_context + self.new_tokens
+        # the window of every stream, packed back to back: [context (oldest first) | new]
+        self._window = torch.zeros(self.n_streams, win, dtype=torch.int64, device=self._device)
+        self._filled = 0  # valid context tokens (identical for all streams: they advance together)
+        self._graph: torch.cuda.CUDAGraph | None = None
+        self._graph_wav: torch.Tensor | None = None
+        self._steady_steps = 0
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self) -> None:
+        """Start new streams (drops the token history; a captured graph stays valid)."""
+        self._filled = 0
+        self._window.zero_()
+
+    @property
+    def context_tokens(self) -> int:
+        return self._filled
+
+    @torch.no_grad()
+    def push(self, new_ids: torch.Tensor) -> torch.Tensor:
+        """new_ids (n_streams, new_tokens) integer FSQ ids -> (n_streams, new_tokens * samples_per_token)
+        float32 on the decoder's device: the audio of exactly these tokens, given each stream's context."""
+        if new_ids.shape != (self.n_streams, self.new_tokens):
+            raise ValueError(f"new_ids must be ({self.n_streams}, {self.new_tokens})")
+        new_ids = new_ids.to(device=self._device, dtype=torch.int64)
+        n_new, ctx = self.new_tokens, self._filled
+        spt = self.samples_per_token
+        if ctx > 0:
+            # slide: the oldest tokens fall off the left edge of the context
+            keep = min(ctx, self.left_context)
+            self._window[:, self.left_context - keep:self.left_context] = \
+                self._window[:, self.left_context + n_new - keep:self.left_context + n_new].clone()
+        self._window[:, self.left_context:] = new_ids
+        steady = ctx >= self.left_context
+        if steady:
+            wav = self._decode_steady()
+        else:
+            # warm-up of a stream: the window is still growing, shapes change from step to step
+            cur = self._window[:, self.left_context - ctx:].contiguous()
+            wav = self._dec.decode_packed_device(cur.view(-1), [ctx + n_new] * self.n_streams)
+            wav = wav.view(self.n_streams, (ctx + n_new) * spt)
+        out = wav[:, -n_new * spt:].clone()
+        self._filled = min(self.left_context, ctx + n_new)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _decode_steady(self) -> torch.Tensor:
+        win = self.left_context + self.new_tokens
+        seqlens = [win] * self.n_streams
+        if not self._use_graph:
+            return self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
+        if self._graph is None:
+            self._steady_steps += 1
+            if self._steady_steps < 2:
+                # first steady step runs eagerly: plan, workspace and tensor maps of this shape get built
+                return self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
+            stream = torch.cuda.Stream(device=self._device)
+            stream.wait_stream(torch.cuda.current_stream(self._device))
+            with torch.cuda.stream(stream):
+                self._dec.decode_packed_device(self._window.view(-1), seqlens)
+            torch.cuda.current_stream(self._device).wait_stream(stream)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                self._graph_wav = self._dec.decode_packed_device(self._window.view(-1), seqlens)
+            self._graph = graph
+        self._graph.replay()
+        return self._graph_wav.view(self.n_streams, -1)
