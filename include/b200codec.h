@@ -139,6 +139,11 @@ int b200codec_set_attention_impl(int impl);
  * A/B switch; all agree with the fp32 reference, the folds more closely. */
 int b200codec_set_frontend_fold(int mode);
 
+/* GEMM tile width (default on): when M is small (B = 1 serving, BASELINE config 1) the 256-wide tiling
+ * would give only N / 256 of the 74 CTA pairs a tile; 256 x 64 tiles spread the same work over four
+ * times as many. Every output element sees the same K order, so results are bit-identical. A/B switch. */
+int b200codec_set_gemm_narrow_tiles(int on);
+
 /* decode_host with a PINNED output buffer lets the last kernel store the PCM straight into host
  * memory (default on; pageable buffers always take the staged device buffer + copy). A/B switch. */
 int b200codec_set_zero_copy_output(int on);

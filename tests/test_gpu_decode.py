@@ -151,6 +151,27 @@ def test_row_of_batch_equals_single(gpu_decoders):
         assert (batch[b] - single[0]).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item())
 
 
+def test_narrow_gemm_tiles_do_not_change_the_decode(gpu_decoders):
+    """B = 1 and config-1-sized decodes use 256 x 64 GEMM tiles; switching them off must give the very
+    same samples (and therefore the batch invariance above is unaffected by which tiling a batch gets)."""
+    from tts_max_b200 import _lib
+
+    d = gpu_decoders["bf16"]
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(41)
+    cases = [torch.randint(0, 65536, (1, 250), generator=g), torch.randint(0, 65536, (4, 250), generator=g)]
+    try:
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(0))
+        wide = [d(c.cuda()).clone() for c in cases]
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(1))
+        narrow = [d(c.cuda()).clone() for c in cases]
+    finally:
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(1))
+    for a, b in zip(wide, narrow):
+        # identical GEMM results; only the fp64 GroupNorm atomics may reorder
+        assert (a - b).abs().max().item() <= 1e-6 * max(1e-3, a.abs().max().item())
+
+
 def test_determinism(gpu_decoders):
     d = gpu_decoders["bf16"]
     ids = torch.randint(0, 65536, (2, 300), generator=torch.Generator().manual_seed(9)).cuda()

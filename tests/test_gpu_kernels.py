@@ -126,6 +126,30 @@ def test_gemm_implicit_conv(prec, taps, M):
     assert err <= 3e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
 
 
+@pytest.mark.parametrize("M,N,K,taps", [(1, 1024, 1024, 1), (250, 1024, 4096, 1), (253, 3072, 1024, 1),
+                                         (500, 1024, 1024, 3), (1009, 1024, 1024, 1)])
+def test_gemm_narrow_tiles_are_invisible(M, N, K, taps):
+    """Small M runs on 256 x 64 tiles; every output element sees the same K order, so the result is
+    bit-identical to the 256-wide tiling (fp32 + residual and 16-bit + SiLU epilogues)."""
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, taps * K, device="cuda", generator=g) / (taps * K) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    try:
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(0))
+        wide32 = gemm("bf16", a, w, taps=taps, bias=bias, residual=res)
+        wide16 = gemm("bf16", a, w, taps=taps, out_fp32=False, bias=bias, act=1)
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(1))
+        narrow32 = gemm("bf16", a, w, taps=taps, bias=bias, residual=res)
+        narrow16 = gemm("bf16", a, w, taps=taps, out_fp32=False, bias=bias, act=1)
+    finally:
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(1))
+    assert torch.isfinite(narrow32).all()
+    assert torch.equal(wide32, narrow32) and torch.equal(wide16, narrow16)
+
+
 # ----------------------------------------------------------------------------------------------
 # norms
 # ----------------------------------------------------------------------------------------------

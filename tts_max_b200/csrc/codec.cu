@@ -23,6 +23,7 @@
 #include "kernels.h"
 
 namespace b200 {
+extern int g_gemm_narrow_tiles;  // gemm_tc05.cu: 256 x 64 tiles for small M (default on)
 
 int g_use_pdl = 1;
 // ids -> embed output: 1 = folded, im2col of the codes + one K = 128 tensor-core GEMM (default);
@@ -443,7 +444,7 @@ int ensure_workspace(B200Codec* h, int rows) {
     const size_t Rlast = R * h->total_up;  // rows of the last (upsampled) row space
     size_t sz_c = al(R * C * es), sz_qkv = al(R * 3 * C * es),
            sz_f = al(R * 4 * C * es), sz_x = al(R * C * 4), sz_ho = al(Rlast * h->head_ld * 4);
-    size_t sz_ss = al(R * 8 * 4);
+    size_t sz_ss = al(R * 32 * 4);  // kGemmSsSlots row partials
     size_t total = 4 * sz_c + sz_qkv + sz_f + 2 * sz_x + sz_ho + sz_ss;
     size_t up_rows[kMaxUp], sz_up32[kMaxUp], sz_up16[kMaxUp];
     {
@@ -1443,6 +1444,11 @@ int b200codec_set_frontend_fold(int mode) {
     B200_CHECK(mode >= 0 && mode <= 2, "front-end mode must be 0 (lookup + conv7 GEMM), 1 (folded, tensor cores) "
                                        "or 2 (folded, fp32 FMA kernel)");
     g_frontend_fold = mode;
+    return 0;
+}
+
+int b200codec_set_gemm_narrow_tiles(int on) {
+    g_gemm_narrow_tiles = on != 0;
     return 0;
 }
 

@@ -227,6 +227,8 @@ int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out) {
 unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
 #endif
 
+int g_gemm_narrow_tiles = 1;  // A/B: 0 = 256-wide tiles only
+
 int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     B200_CHECK(c.precision == kPrecBf16 || c.precision == kPrecFp16,
                "gemm: unsupported precision %d", c.precision);
@@ -294,6 +296,28 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
                 return 1;
         } else {
             if (make_tmap_box(&to16, c.out, dt16, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
+        }
+        // Small M: 256 x 64 tiles when the 256-wide tiling would leave most CTA pairs without a tile
+        // (B = 1 serving, config 1). A narrow tile costs ~0.6 of a wide one (its K loop is bounded by
+        // the A-tile load), so it pays when four times the tiles still fit in fewer weighted rounds.
+        const int pairs = kNumSMs / 2;
+        const int tiles256 = ((c.a_rows + 255) / 256) * (c.n_store / 256);
+        const int rounds256 = (tiles256 + pairs - 1) / pairs;
+        const int rounds64 = (4 * tiles256 + pairs - 1) / pairs;
+        const bool narrow = g_gemm_narrow_tiles && c.tmap_b == nullptr && rounds64 * 60 < rounds256 * 95;
+        if (narrow) {
+            const int dtb = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
+            if (make_tmap_2d(&tb, c.w, dtb, c.N, static_cast<uint64_t>(c.taps) * c.Cin,
+                             static_cast<uint64_t>(c.taps) * c.Cin, 32))
+                return 1;
+            if (p.gn_stats != nullptr) {
+                if (c.precision == kPrecBf16)
+                    return launch_gemm_tc05_2cta<__nv_bfloat16, true, 64>(ta, tb, to32, to16, p, stream);
+                return launch_gemm_tc05_2cta<__half, true, 64>(ta, tb, to32, to16, p, stream);
+            }
+            if (c.precision == kPrecBf16)
+                return launch_gemm_tc05_2cta<__nv_bfloat16, false, 64>(ta, tb, to32, to16, p, stream);
+            return launch_gemm_tc05_2cta<__half, false, 64>(ta, tb, to32, to16, p, stream);
         }
         if (p.gn_stats != nullptr) {
             if (c.precision == kPrecBf16)

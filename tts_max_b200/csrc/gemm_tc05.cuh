@@ -46,13 +46,13 @@ struct GemmParams {
     int act;
     // ---- RMSNorm fusion (CTA-pair kernel only) ----
     // consumer: out = act(rstd[m] * acc + bias), rstd[m] = rsqrt(sum_s ss_in[m][s] * ss_inv_dim + ss_eps)
-    const float* ss_in;    // [M][8] partial sums of x^2 (one per 128 columns of the 1024-wide x) or nullptr
+    const float* ss_in;    // [M][32] partial sums of x^2 (one per 32 columns of the 1024-wide x) or nullptr
     float ss_inv_dim;
     float ss_eps;
     // producer (fp32-output GEMMs): also write the 16-bit copy of the result and its row partial sums
     void* out16;           // [M, ld16] operand dtype or nullptr
     int ld16;
-    float* ss_out;         // [M][8] or nullptr; slot = column / 128 (requires N == 1024)
+    float* ss_out;         // [M][32] or nullptr; slot = column / 32 (requires N == 1024)
     // CTA-pair kernel: which outputs exist (their addresses travel in tensor maps)
     int has32;             // fp32 `out` (+ optional residual)
     int has16;             // 16-bit `out` (has32 == 0) or the 16-bit copy `out16` (has32 == 1)
@@ -79,6 +79,7 @@ struct GemmParams {
 #define B200_TRACE(slot) do { } while (0)
 #endif
 
+constexpr int kGemmSsSlots = 32;  // row sum-of-squares partials per row (fused RMSNorm)
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmThreads = 256;
 

@@ -127,18 +127,25 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
 // tmap_o16: 16-bit [M, n_store] output or operand copy, box 32 x 32, SWIZZLE_64B (p.has16).
 // kGnStats: the instantiation that also reduces GroupNorm statistics (p.gn_stats), kept apart so the
 // extra registers do not touch the common kernel.
-template <typename InT, bool kGnStats>
+// BLOCK_N: 256, or 64 for small M: with one to a few m-blocks only N / 256 of the 74 CTA pairs would
+// have a tile and each would walk the whole K loop alone; 256 x 64 tiles put four times as many pairs
+// to work (the K loop of a narrow tile is bounded by the A-tile load, ~0.15 us per K-block instead of
+// 0.26). Every output element sees the same K order, so the tile width never changes results. The
+// shared-memory stage keeps its 256-wide size; TMEM holds 2 x BLOCK_N columns.
+template <typename InT, bool kGnStats, int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_o32,
                       const __grid_constant__ CUtensorMap tmap_o16, const GemmParams p) {
     using SM = Gemm2Smem;
-    constexpr int BLOCK_N = kGemm2BlockN;
+    static_assert(BLOCK_N == 256 || BLOCK_N == 64, "tile width");
+    constexpr int kHalfN = BLOCK_N / 2;  // B rows staged by each CTA = accumulator columns per epilogue warp
+    constexpr uint32_t kStageTx = 2 * (SM::kABytes + kHalfN * 128);  // bytes both CTAs land per stage
     constexpr int BLOCK_K = 64;
     constexpr int UMMA_K = 16;
     constexpr int kStages = kGemm2Stages;
-    constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages of 256 fp32 columns
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages of BLOCK_N fp32 columns (512 or 128)
     static_assert(sizeof(InT) == 2, "2-CTA kernel is instantiated for bf16 / fp16 operands");
 
     extern __shared__ uint8_t smem_raw[];
@@ -202,11 +209,11 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 const int n_blk = tile % num_n;
                 const int m_blk = tile / num_n;
                 const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
-                const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * 128;
+                const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * kHalfN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     // both CTAs' bytes complete on the leader's barrier
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::kStageBytes);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
                     const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
                     const int tap = kb / p.k_blocks_per_tap;
                     const int kc = kb - tap * p.k_blocks_per_tap;
@@ -270,7 +277,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // at slot j ^ (r & 7) of its 128-byte fp32 row and at slot j ^ ((r >> 1) & 3) of its
         // 64-byte 16-bit row.
         constexpr int CH = kGemm2ChunkCols;
-        constexpr int kChunks = 128 / CH;
+        constexpr int kChunks = kHalfN / CH;
         const int ew = warp - 4;
         const int q = warp & 3;   // TMEM lane quarter
         const int hh = ew >> 2;   // which 128-column half of the tile
@@ -306,7 +313,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int o = 16; o > 0; o >>= 1) gn_u0 = max(gn_u0, __shfl_xor_sync(0xffffffffu, gn_u0, o));
                 gn_uniform = __all_sync(0xffffffffu, gn_utt < 0 || gn_utt == gn_u0);
             }
-            const int ncol0 = n_blk * BLOCK_N + hh * 128;
+            const int ncol0 = n_blk * BLOCK_N + hh * kHalfN;
             // this lane's residual row: 128 contiguous bytes per chunk, fetched as whole sectors
             const float* res_row = has_res && row_ok
                                        ? p.residual + static_cast<size_t>(row) * p.ld_res + ncol0
@@ -328,17 +335,22 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // fused RMSNorm, consumer side: per-row 1/rms from the producer's eight partial sums
             float rscale = 1.f;
             if (p.ss_in != nullptr && row_ok) {
-                const float4* sp = reinterpret_cast<const float4*>(p.ss_in + static_cast<size_t>(row) * 8);
-                const float4 s0 = sp[0], s1 = sp[1];
-                const float tot = ((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w));
+                // 32 partial sums (one per 32-column chunk of the 1024-wide x), added in a fixed order that
+                // does not depend on the tile width of the GEMM that produced them
+                const float4* sp = reinterpret_cast<const float4*>(p.ss_in + static_cast<size_t>(row) * kGemmSsSlots);
+                float tot = 0.f;
+#pragma unroll
+                for (int i = 0; i < kGemmSsSlots / 4; ++i) {
+                    const float4 s4 = sp[i];
+                    tot += (s4.x + s4.y) + (s4.z + s4.w);
+                }
                 rscale = rsqrtf(tot * p.ss_inv_dim + p.ss_eps);
             }
-            float ssq = 0.f;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc05_fence_after();
             if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(10 + 2 * trace_tile);  // accumulator ready
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                    static_cast<uint32_t>(acc * BLOCK_N + hh * 128);
+                                    static_cast<uint32_t>(acc * BLOCK_N + hh * kHalfN);
             uint32_t r_next[CH];
             tmem_ld_32x32(t_base, r_next);  // chunk c+1 is in flight while chunk c is processed
 #pragma unroll
@@ -438,8 +450,10 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                     // fused RMSNorm, producer side: row sum of squares (fixed order)
                     if (p.ss_out != nullptr) {
+                        float cs = 0.f;
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) ssq = fmaf(v[j], v[j], ssq);
+                        for (int j = 0; j < CH; ++j) cs = fmaf(v[j], v[j], cs);
+                        if (row_ok) p.ss_out[static_cast<size_t>(row) * kGemmSsSlots + (n0 >> 5)] = cs;  // one slot per chunk
                     }
                 }
                 if (has16) {
@@ -468,8 +482,6 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(11 + 2 * trace_tile);  // tile drained
             ++trace_tile;
-            if (has32 && p.ss_out != nullptr && row_ok)
-                p.ss_out[static_cast<size_t>(row) * 8 + (ncol0 >> 7)] = ssq;  // one slot per 128 columns
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -489,17 +501,17 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
-template <typename InT, bool kGnStats>
+template <typename InT, bool kGnStats, int BLOCK_N = kGemm2BlockN>
 int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to32,
                           const CUtensorMap& to16, const GemmParams& p, cudaStream_t stream) {
-    auto kern = gemm_tc05_2cta_kernel<InT, kGnStats>;
+    auto kern = gemm_tc05_2cta_kernel<InT, kGnStats, BLOCK_N>;
     static PerDeviceOnce once;
     if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Gemm2Smem::kTotal));
     }
     const int num_m = (p.M + 255) / 256;
-    const int num_n = p.n_store / kGemm2BlockN;
+    const int num_n = p.n_store / BLOCK_N;
     int clusters = num_m * num_n;
     if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
     if (clusters < 1) return 0;
