@@ -255,33 +255,58 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
         stockham_pass<kHalf / 64, kHalf>(sm.buf_b, sm.buf_a, sm.tw, 64);  // radix 10 (640) or 5 (320)
         __syncthreads();
 
-        // 4. window, 1/n_fft and overlap-add (gather form: one thread per output sample).
+        // 4. window, 1/n_fft and overlap-add. A thread owns the output samples n = tid (mod 256) in every
+        //    frame (no write conflicts, no extra barrier) and walks, per frame, only the samples that
+        //    frame covers; frames are added in ascending order, as before.
         //    buf_a[f] viewed as 1280 floats is the time-domain frame: x[2n] = Re z[n], x[2n+1] = Im z[n].
-        for (int n = threadIdx.x; n < kIstftOutHops * kHop; n += kIstftThreads) {
-            float acc = sm.ola[n];
 #pragma unroll
-            for (int f = 0; f < kGroup; ++f) {
-                const int t = t_first + f;
-                // frame t covers output samples [320 t - 480, 320 t + 800); n is relative to 320 b0
-                const int m = n + kPad - kHop * (t - b0);
-                if (t >= 0 && t < T && m >= 0 && m < kNfft)
-                    acc += reinterpret_cast<const float*>(sm.buf_a[f])[m] * (1.f / kNfft) * sm.win[m];
+        for (int f = 0; f < kGroup; ++f) {
+            const int t = t_first + f;
+            if (t < 0 || t >= T) continue;  // uniform
+            // frame t covers output samples [hop * t - pad, hop * t - pad + n_fft); o = that start
+            // relative to this tile's first sample hop * b0
+            const int o = kHop * (t - b0) - kPad;
+            const int lo = max(o, 0), hi = min(o + kNfft, kIstftOutHops * kHop);
+            const float* xf = reinterpret_cast<const float*>(sm.buf_a[f]);
+            // first n >= lo with n = tid (mod 256)
+            int n = lo + ((static_cast<int>(threadIdx.x) - lo) & (kIstftThreads - 1));
+            for (; n < hi; n += kIstftThreads) {
+                const int m = n - o;
+                sm.ola[n] += xf[m] * (1.f / kNfft) * sm.win[m];
             }
-            sm.ola[n] = acc;
         }
         __syncthreads();
     }
 
-    // 5. normalise by the overlap-added squared window (edges see fewer frames) and store
-    const int n_out = min(kIstftOutHops, T - b0) * kHop;
-    for (int n = threadIdx.x; n < n_out; n += kIstftThreads) {
-        const int b = b0 + n / kHop;
+    // 5. normalise by the overlap-added squared window and store. A hop whose five frames b-2 .. b+2 all
+    //    exist sees the same envelope (a function of n mod hop, summed in the same dt order); only the
+    //    two hops at either end of an utterance take the general path.
+    float* env_hop = reinterpret_cast<float*>(sm.buf_b);  // buf_b is free after the last group
+    for (int j = threadIdx.x; j < kHop; j += kIstftThreads) {
         float env = 0.f;
 #pragma unroll
         for (int dt = -2; dt <= 2; ++dt) {
-            const int t = b + dt;
-            const int m = n + kPad - kHop * (t - b0);
-            if (t >= 0 && t < T && m >= 0 && m < kNfft) env = fmaf(sm.win[m], sm.win[m], env);
+            const int m = j + kPad - kHop * dt;
+            if (m >= 0 && m < kNfft) env = fmaf(sm.win[m], sm.win[m], env);
+        }
+        env_hop[j] = env;
+    }
+    __syncthreads();
+    const int n_out = min(kIstftOutHops, T - b0) * kHop;
+    for (int n = threadIdx.x; n < n_out; n += kIstftThreads) {
+        const int hb = n / kHop;
+        const int b = b0 + hb;
+        float env;
+        if (b >= 2 && b + 2 < T) {
+            env = env_hop[n - hb * kHop];
+        } else {
+            env = 0.f;
+#pragma unroll
+            for (int dt = -2; dt <= 2; ++dt) {
+                const int t = b + dt;
+                const int m = n + kPad - kHop * (t - b0);
+                if (t >= 0 && t < T && m >= 0 && m < kNfft) env = fmaf(sm.win[m], sm.win[m], env);
+            }
         }
         wav_u[static_cast<size_t>(b0) * kHop + n] = sm.ola[n] / env;
     }
