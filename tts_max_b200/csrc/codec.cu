@@ -533,6 +533,8 @@ struct NormFuse {
     void* out16 = nullptr;         // produce: 16-bit copy of the fp32 result ...
     float* ss_out = nullptr;       // ... and its per-row sum-of-squares partials
     double* gn_stats = nullptr;    // produce: GroupNorm statistics of the fp32 result (N == 1024 only)
+    float out16_scale = 1.f;       // produce: power-of-two scale of the 16-bit copy (fp16 operands)
+    float ss_in_scale = 1.f;       // consume: its inverse
 };
 
 int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
@@ -563,11 +565,14 @@ int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, v
     c.ss_out = nf.ss_out;
     c.gn_stats = nf.gn_stats;
     c.gn_row_utt = h->rs.row_utt;
+    c.out16_scale = nf.out16_scale;
+    c.ss_in_scale = nf.ss_in_scale;
     return launch_gemm(c, s);
 }
 
 // ResnetBlock (decoder_modules.py:201-223) on one row space at C channels:
 //   x <- x + conv2(swish(GN2(conv1(swish(GN1(x))))))
+static bool g_fuse_rmsnorm = true;  // RMSNorm inside the GEMM epilogues (false: stand-alone kernel)
 static bool g_gn_in_gemm = true;  // GroupNorm statistics reduced in the producing GEMM's epilogue
 static bool gn_stats_in_gemm(int rows, int C) {
     return g_gn_in_gemm && C == 1024 && gemm_uses_cta_pairs(rows, C);
@@ -618,6 +623,8 @@ int resnet_block_ex(B200Codec* h, const ResCtx& cx, const ResBlockW& w, int stat
         c.ss_out = f.ss_out;
         c.gn_stats = f.gn_stats;
         c.gn_row_utt = rs.row_utt;
+        c.out16_scale = f.out16_scale;
+        c.ss_in_scale = f.ss_in_scale;
         return launch_gemm(c, s);
     };
     // the conv GEMMs reduce the statistics of what they write when a chunk of their epilogue is a
@@ -797,16 +804,21 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
                      h->m("decoder.backbone.embed.bias"), nullptr, kActNone, false, s));
         }
     }
-    // RMSNorm fusion (bf16 operands, CTA-pair GEMM): the GEMM that produces the residual stream x
-    // also emits bf16(x) and per-row sum-of-squares partials; the norm weight lives in the columns
-    // of c_attn / fc1 and rstd[row] is applied in their epilogues. fp16 operands keep a standalone
-    // normalisation (un-normalised activations could leave fp16's range).
-    const bool fuse_rms = prec == kPrecBf16 && gemm_uses_cta_pairs(rs.rows, C);
+    // RMSNorm fusion (CTA-pair GEMM): the GEMM that produces the residual stream x also emits a 16-bit
+    // copy of x and per-row sum-of-squares partials; the norm weight lives in the columns of c_attn /
+    // fc1 and rstd[row] is applied in their epilogues. With fp16 operands the copy is x / 64 (exact;
+    // un-normalised activations up to 4e6 stay inside fp16's range) and the consumers' row scale
+    // carries the factor 64 back -- RMSNorm does not care about the scale of its input.
+    const bool fuse_rms = g_fuse_rmsnorm && gemm_uses_cta_pairs(rs.rows, C);
     NormFuse produce, consume;
     if (fuse_rms) {
         produce.out16 = h->xb;
         produce.ss_out = h->ss;
         consume.ss_in = h->ss;
+        if (prec == kPrecFp16) {
+            produce.out16_scale = 1.f / 64.f;
+            consume.ss_in_scale = 64.f;
+        }
     }
     if (resnet_block(h, h->res[0], 0, s, NormFuse(), gn0_done, gn_slot(2))) return 1;
     if (resnet_block(h, h->res[1], 2, s, produce, gn_fused, nullptr)) return 1;

@@ -263,6 +263,8 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     p.out16 = c.out16;
     p.ld16 = c.ld16;
     p.ss_out = c.ss_out;
+    p.out16_scale = c.out16_scale;
+    p.ss_in_scale = c.ss_in_scale;
 #ifdef B200_GEMM_TRACE
     p.trace = g_gemm_trace;
 #endif

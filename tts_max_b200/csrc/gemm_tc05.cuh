@@ -53,6 +53,11 @@ struct GemmParams {
     void* out16;           // [M, ld16] operand dtype or nullptr
     int ld16;
     float* ss_out;         // [M][32] or nullptr; slot = column / 32 (requires N == 1024)
+    // fp16 operands: the copy is stored as x * out16_scale (a power of two, so un-normalised activations
+    // cannot leave fp16's range) and the consumer multiplies its row scale by ss_in_scale = 1 / out16_scale
+    // (RMSNorm is scale-invariant; both factors are exact). 1 for bf16.
+    float out16_scale;
+    float ss_in_scale;
     // CTA-pair kernel: which outputs exist (their addresses travel in tensor maps)
     int has32;             // fp32 `out` (+ optional residual)
     int has16;             // 16-bit `out` (has32 == 0) or the 16-bit copy `out16` (has32 == 1)

@@ -344,7 +344,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const float4 s4 = sp[i];
                     tot += (s4.x + s4.y) + (s4.z + s4.w);
                 }
-                rscale = rsqrtf(tot * p.ss_inv_dim + p.ss_eps);
+                rscale = rsqrtf(tot * p.ss_inv_dim + p.ss_eps) * p.ss_in_scale;
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc05_fence_after();
@@ -457,13 +457,15 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
                 if (has16) {
+                    // the 16-bit COPY of an fp32 result may carry a power-of-two scale (see out16_scale)
+                    const float s16 = has32 ? p.out16_scale : 1.f;
 #pragma unroll
                     for (int j = 0; j < CH / 8; ++j)
                         sts_128(buf16 + row16 + ((static_cast<uint32_t>(j) ^ swz16) << 4),
-                                Half16<InT>::pack(v[8 * j + 0], v[8 * j + 1]),
-                                Half16<InT>::pack(v[8 * j + 2], v[8 * j + 3]),
-                                Half16<InT>::pack(v[8 * j + 4], v[8 * j + 5]),
-                                Half16<InT>::pack(v[8 * j + 6], v[8 * j + 7]));
+                                Half16<InT>::pack(v[8 * j + 0] * s16, v[8 * j + 1] * s16),
+                                Half16<InT>::pack(v[8 * j + 2] * s16, v[8 * j + 3] * s16),
+                                Half16<InT>::pack(v[8 * j + 4] * s16, v[8 * j + 5] * s16),
+                                Half16<InT>::pack(v[8 * j + 6] * s16, v[8 * j + 7] * s16));
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();

@@ -115,6 +115,8 @@ struct GemmCall {
     void* out16 = nullptr;
     int ld16 = 0;
     float* ss_out = nullptr;
+    float out16_scale = 1.f;  // power of two applied to the 16-bit copy (fp16 operands), see GemmParams
+    float ss_in_scale = 1.f;  // its inverse, applied with the consumer's row scale
     // optional pre-encoded TMA descriptors (CUtensorMap, 128 B each, 64-byte aligned);
     // when null they are encoded on the fly.
     const void* tmap_a = nullptr;
