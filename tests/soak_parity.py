@@ -1,3 +1,5 @@
+"""Randomised parity / batch-invariance soak (run by hand on a B200: `python tests/soak_parity.py`).
+Lives under tests/ because it uses the oracle; not collected by pytest."""
 import sys, torch, random
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tts_max_b200.codec import decoder
