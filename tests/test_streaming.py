@@ -19,6 +19,26 @@ def test_streaming_requires_cuda_decoder():
         streaming.StreamingDecoder(dec, n_streams=0)
 
 
+@pytest.mark.parametrize("ctx_len,new", [(20, 10), (25, 10), (5, 10), (0, 7), (30, 30)])
+def test_window_slide_logic(ctx_len, new):
+    """The device-side token history: after every push the window holds exactly the last
+    min(ctx_len, pushed) tokens (right-aligned) followed by the new ones."""
+    from tts_max_b200.codec import streaming
+
+    g = torch.Generator().manual_seed(ctx_len * 100 + new)
+    ids = torch.randint(0, 65536, (2, new * 9), generator=g)
+    window = torch.zeros(2, ctx_len + new, dtype=torch.int64)
+    filled = 0
+    for k in range(9):
+        chunk = ids[:, k * new:(k + 1) * new]
+        nxt = streaming.slide_window(window, filled, ctx_len, chunk)
+        lo = max(0, k * new - ctx_len)
+        want = ids[:, lo:(k + 1) * new]
+        assert torch.equal(window[:, ctx_len + new - want.shape[1]:], want), k
+        assert filled == min(ctx_len, k * new)
+        filled = nxt
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_push_equals_window_decode(gpu_decoders, state_dict, use_graph):

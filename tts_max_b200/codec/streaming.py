@@ -23,6 +23,19 @@ import torch
 from tts_max_b200.codec import decoder as decoder_lib
 
 
+def slide_window(window: torch.Tensor, filled: int, left_context: int, new_ids: torch.Tensor) -> int:
+    """In-place update of the (n_streams, left_context + new) window `[context | new]`: the context
+    becomes the last `filled` tokens of what the window held (right-aligned), the new tokens go in
+    behind it. Returns the context length valid for the NEXT push."""
+    n_new = new_ids.shape[1]
+    if filled > 0:
+        keep = min(filled, left_context)
+        window[:, left_context - keep:left_context] = \
+            window[:, left_context + n_new - keep:left_context + n_new].clone()
+    window[:, left_context:] = new_ids
+    return min(left_context, filled + n_new)
+
+
 class StreamingDecoder:
     """`n_streams` independent streams advancing in lock step, `new_tokens` tokens per `push`."""
 
@@ -66,12 +79,7 @@ class StreamingDecoder:
         new_ids = new_ids.to(device=self._device, dtype=torch.int64)
         n_new, ctx = self.new_tokens, self._filled
         spt = self.samples_per_token
-        if ctx > 0:
-            # slide: the oldest tokens fall off the left edge of the context
-            keep = min(ctx, self.left_context)
-            self._window[:, self.left_context - keep:self.left_context] = \
-                self._window[:, self.left_context + n_new - keep:self.left_context + n_new].clone()
-        self._window[:, self.left_context:] = new_ids
+        next_filled = slide_window(self._window, ctx, self.left_context, new_ids)
         steady = ctx >= self.left_context
         if steady:
             wav = self._decode_steady()
@@ -81,7 +89,7 @@ class StreamingDecoder:
             wav = self._dec.decode_packed_device(cur.view(-1), [ctx + n_new] * self.n_streams)
             wav = wav.view(self.n_streams, (ctx + n_new) * spt)
         out = wav[:, -n_new * spt:].clone()
-        self._filled = min(self.left_context, ctx + n_new)
+        self._filled = next_filled
         return out
 
     # ------------------------------------------------------------------------------------------
