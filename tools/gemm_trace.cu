@@ -129,7 +129,7 @@ int main(int argc, char** argv) {
     printf("first CTA start -> last CTA exit: %.2f us\n", (t_end - t0) * 1e-3);
     static const char* names[32] = {"start", "prologue", "ops0", "mma0", "ops1", "mma1", "ops2", "mma2",
                                     "ops3", "mma3", "acc0", "drain0", "acc1", "drain1", "acc2", "drain2",
-                                    "acc3", "drain3", "", "", "exit"};
+                                    "acc3", "drain3", "", "", "exit", "bar_init", "alloc_in", "alloc_out"};
     // order leader CTAs by exit time; print the fastest, the median and the slowest pair
     std::vector<int> leaders;
     for (int b = 0; b < grid; b += 2) leaders.push_back(b);
@@ -137,7 +137,7 @@ int main(int argc, char** argv) {
     const int picks[1] = {leaders.back()};
     for (int b : picks) {
         printf("CTA %3d (leader) / %3d (peer):\n", b, b + 1);
-        for (int s = 0; s <= 20; ++s) {
+        for (int s = 0; s <= 23; ++s) {
             if (names[s][0] == 0) continue;
             const unsigned long long tl = h[b * 128 + s], tp = h[(b + 1) * 128 + s];
             if (tl == 0 && tp == 0) continue;

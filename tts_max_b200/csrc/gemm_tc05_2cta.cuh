@@ -64,6 +64,13 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only cluster barrier. The release form costs a MEMBAR.GPU (~0.3-0.5 us, tools/gemm_trace.cu)
+// and this kernel never needs it: mbarrier initialisation is published by fence.mbarrier_init, the TMEM
+// slot is CTA-local (a __syncthreads orders it), and at exit only "nobody leaves early" matters.
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank`
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
     uint32_t r;
@@ -189,10 +196,16 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_init(&tmem_empty[s], 16);  // leader's: 8 epilogue warps x 2 CTAs
         }
         fence_barrier_init();
+        B200_TRACE(21);
     }
-    if (warp == 2) tmem_alloc_2cta<kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if (lane == 0) B200_TRACE(22);
+        tmem_alloc_2cta<kTmemCols>(tmem_slot);
+        if (lane == 0) B200_TRACE(23);
+    }
     tc05_fence_before();
-    cluster_sync_all();  // peer barriers initialised, TMEM allocated in both CTAs
+    __syncthreads();         // this CTA's barriers and TMEM slot
+    cluster_sync_relaxed();  // peer barriers initialised, TMEM allocated in both CTAs
     tc05_fence_after();
     if (threadIdx.x == 0) B200_TRACE(1);
     pdl_wait();  // barrier init, TMEM allocation and the cluster sync overlap the predecessor's tail
@@ -497,7 +510,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     // the leader's MMAs read the peer's shared memory: neither CTA may exit early
     tc05_fence_before();
-    cluster_sync_all();
+    cluster_sync_relaxed();
     tc05_fence_after();
     if (threadIdx.x == 0) B200_TRACE(20);
     if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
