@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&out, static_cast<size_t>(M) * N * 4);
     cudaMalloc(&res, static_cast<size_t>(M) * N * 4);
     cudaMalloc(&o16, static_cast<size_t>(M) * N * 2);
-    cudaMalloc(&ss, static_cast<size_t>(M) * 8 * 4);
+    cudaMalloc(&ss, static_cast<size_t>(M) * b200::kGemmSsSlots * 4);
     const int grid = 148;
     cudaMalloc(&trace, grid * 128 * 8);
     fill_kernel<<<1024, 256>>>(a, static_cast<size_t>(M + 2 * halo) * K, 1);
@@ -126,6 +126,9 @@ int main(int argc, char** argv) {
         if (h[b * 128 + 0]) t0 = std::min(t0, h[b * 128 + 0]);
         t_end = std::max(t_end, h[b * 128 + 20]);
     }
+    int missing = 0;
+    for (int b = 0; b < grid; ++b) missing += h[b * 128 + 20] == 0;
+    if (missing) printf("%d CTAs left no exit stamp\n", missing);
     printf("first CTA start -> last CTA exit: %.2f us\n", (t_end - t0) * 1e-3);
     static const char* names[32] = {"start", "prologue", "ops0", "mma0", "ops1", "mma1", "ops2", "mma2",
                                     "ops3", "mma3", "acc0", "drain0", "acc1", "drain1", "acc2", "drain2",
