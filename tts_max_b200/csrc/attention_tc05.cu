@@ -103,6 +103,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     uint64_t* bar_s_full = bar_q + 3;
     uint64_t* bar_p_full = bar_q + 4;
     uint64_t* bar_o_full = bar_q + 5;
+    uint64_t* bar_s_read = bar_q + 6;    // every softmax thread holds S_j in registers: S may be overwritten
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 8);
     float* red = reinterpret_cast<float*>(smem + AttnSmem::kRed);  // [2 parities][2 halves][128 rows]
 
@@ -128,6 +129,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         mbar_init(bar_s_full, 1);
         mbar_init(bar_p_full, kSoftmaxThreads);
         mbar_init(bar_o_full, 1);
+        mbar_init(bar_s_read, kSoftmaxThreads);
         fence_barrier_init();
     }
     __syncwarp();
@@ -175,16 +177,20 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
             ATTN_TRACE(2);
             issue_s(0);
             for (int j = 0; j < n_kv; ++j) {
-                // every row's P_j is in TMEM, S_j has been read and O rescaled: next S first (the
-                // softmax warps are waiting for it), then O += P_j V_j behind it
-                mbar_wait(bar_p_full, j & 1);
-                tc05_fence_after();
-                if (j < 6) ATTN_TRACE(8 + j * 8 + 5);  // every row's P_j stored
+                // S_{j+1} only needs S_j out of tensor memory (it sits in the softmax threads'
+                // registers as soon as their tcgen05.ld completes), not P_j: issue it during the
+                // exponentials, so that it is ready when the softmax warps come back for it
                 if (j + 1 < n_kv) {
+                    mbar_wait(bar_s_read, j & 1);
+                    tc05_fence_after();
                     mbar_wait(&bar_kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
                     tc05_fence_after();
                     issue_s(j + 1);
                 }
+                // every row's P_j is in TMEM and O rescaled: O += P_j V_j
+                mbar_wait(bar_p_full, j & 1);
+                tc05_fence_after();
+                if (j < 6) ATTN_TRACE(8 + j * 8 + 5);  // every row's P_j stored
                 const uint32_t v_base = smem_u32(sV + (j & 1) * kTileBytes);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
@@ -220,6 +226,8 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
         tmem_ld_32x32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
         tmem_ld_32x32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
         tmem_ld_wait();
+        tc05_fence_before();
+        mbar_arrive(bar_s_read);
         if (j < 6) ATTN_TRACE(8 + j * 8 + 1);  // S_j in registers
         if (!full) {
 #pragma unroll
