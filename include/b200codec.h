@@ -18,6 +18,11 @@
  *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
  *     ordinary (ideally pinned) host memory.
  *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels.
+ *   - Threading: a handle owns ONE plan, workspace and staging area, so it decodes one batch at a
+ *     time. The decode entry points take a per-handle mutex (concurrent callers serialise), and a
+ *     handle must be used with one stream at a time: work a previous decode left in flight on
+ *     ANOTHER stream is not waited for before buffers are rebuilt. Several handles per process are
+ *     independent (the reference makes up to three decoders per process, rewards.py:36-38).
  */
 #ifndef B200CODEC_H_
 #define B200CODEC_H_
@@ -32,14 +37,14 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B200CODEC_ABI_VERSION 2
+#define B200CODEC_ABI_VERSION 3
 
 /* arithmetic type of the tensor-core operands (accumulation is always fp32; the residual
  * stream, norms, softmax, FSQ lookup and ISTFT are always fp32). */
 enum B200CodecPrecision {
     B200CODEC_BF16 = 0, /* tcgen05 kind::f16, bf16 operands (BASELINE config 2 "bf16 decode") */
-    B200CODEC_FP16 = 1, /* tcgen05 kind::f16, fp16 operands (same rate, 3 more mantissa bits) */
-    B200CODEC_TF32 = 2  /* tcgen05 kind::tf32, fp32 storage (half rate; "fp32-tolerance" mode) */
+    B200CODEC_FP16 = 1  /* tcgen05 kind::f16, fp16 operands (same rate, 3 more mantissa bits): the
+                           high-precision mode, >= 55 dB against the fp32 reference */
 };
 
 /* element type of the ids passed to the lookup / decode entry points */
@@ -126,6 +131,26 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
  * After synchronising the stream, this returns 1 if any decode since the last call saw such
  * an id (and clears the flag). decode_host checks on the host instead and fails up front. */
 int b200codec_take_id_error(B200Codec* h);
+
+/* Monotonic counter, bumped whenever a decode rebuilt or reallocated the handle's plan, workspace or
+ * statistics buffers (a new batch shape, a larger batch). A CUDA graph captured from decode_varlen
+ * bakes those device pointers and the plan contents in: replay it only while the value is the one
+ * seen right after capture, otherwise decode eagerly and capture again
+ * (tts_max_b200/codec/streaming.py does exactly that). */
+int64_t b200codec_plan_generation(const B200Codec* h);
+
+/* Debug taps for stage-level parity (tests/test_gpu_decode.py::test_stage_taps_*): when on, every
+ * decode keeps device copies of named stage tensors -- "embed", "prior_net", "tblock0",
+ * "transformers" (fp32 residual stream after backbone.embed / prior_net / transformers[0] / all
+ * transformers, decoder_modules.py:392-396), "backbone" (final_layer_norm output, operand dtype,
+ * :399), "head_linear" (head.out output, :131) and, with an upsampler, "up<i>", "res<i>",
+ * "upsampled" (upsampler.py:62-69). b200codec_read_stage copies one of them to the host as packed
+ * token-major fp32 [rows, width]; b200codec_stage_rows / _width return its shape
+ * (rows = sum(T) x the upsampling reached at that stage; -1: unknown name). Costs device copies per decode; never enable it in a timed run. */
+int b200codec_set_stage_taps(B200Codec* h, int on);
+int b200codec_stage_width(B200Codec* h, const char* name);
+int64_t b200codec_stage_rows(B200Codec* h, const char* name);
+int b200codec_read_stage(B200Codec* h, const char* name, float* host_out, size_t n_elems, void* stream);
 
 /* Process-wide choice of the attention kernel: 0 = tcgen05 / TMEM (default), 1 = the mma.sync
  * flash kernel it replaced (kept for A/B measurements and as a second opinion in the tests). */

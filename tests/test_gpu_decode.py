@@ -1,9 +1,9 @@
 """GPU: the whole decode path through the reference-facing API against the reference's golden
 vectors and the oracle, plus the size-independent properties at BASELINE config sizes.
 
-Stated tolerances (vs the fp32 reference, weights = oracle.weights seed 0):
-  bf16 operands: SNR >= 30 dB and max-abs <= 5e-2 * peak   (BASELINE "bf16 decode" tolerance)
-  fp16 operands: SNR >= 45 dB and max-abs <= 1e-2 * peak
+Stated tolerances (vs the fp32 reference, weights = oracle.weights seed 0; peak |wav| ~ 1.3e-2):
+  bf16 operands: SNR >= 40 dB, max-abs <= 5e-2 * peak and <= 1e-3   (the north star's example bar; measured 44 dB)
+  fp16 operands: SNR >= 55 dB, max-abs <= 1e-2 * peak and <= 1e-3   (measured 62 dB)
 The FSQ lookup inside is bit-exact (tests/test_gpu_kernels.py).
 """
 
@@ -19,7 +19,8 @@ from tts_max_b200.codec import decoder, decoding
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"bf16": (30.0, 5e-2), "fp16": (45.0, 1e-2)}
+TOL = {"bf16": (40.0, 5e-2), "fp16": (55.0, 1e-2)}
+MAX_ABS = 1e-3
 
 
 def check_wave(ref, got, prec, what=""):
@@ -31,6 +32,7 @@ def check_wave(ref, got, prec, what=""):
     assert torch.isfinite(got).all()
     assert snr >= snr_min, f"{what}: SNR {snr:.1f} dB < {snr_min}"
     assert maxabs <= rel * peak, f"{what}: max-abs {maxabs:.3e} > {rel} * peak {peak:.3e}"
+    assert maxabs <= MAX_ABS, f"{what}: max-abs {maxabs:.3e} > {MAX_ABS}"
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
@@ -261,3 +263,74 @@ def test_many_short_utterances(gpu_decoders):
     single = d.decode_packed_host(utts[150], [lens[150]])
     off = sum(lens[:150])
     assert (packed[off * 320:(off + lens[150]) * 320] - single).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item())
+
+
+# per-stage floors (SNR dB against the reference's own stage tensors). "embed" is the folded front end:
+# exact 16-bit codes x hi/lo-split fp64-folded coefficients, i.e. fp32-like; the others carry 16-bit operands.
+STAGE_SNR = {"bf16": {"embed": 80.0, "default": 40.0}, "fp16": {"embed": 80.0, "default": 55.0}}
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_stage_taps_vs_reference_golden(gpu_decoders, golden, prec):
+    """Stage-level parity ON THE GPU: the debug taps (b200codec_set_stage_taps / _read_stage) against the
+    reference's forward-hook captures in the golden file (oracle/make_golden.py: embed, prior_net,
+    transformers[0], all transformers, backbone, head.out; decoder_modules.py:390-400, :131), so
+    compensating errors between stages cannot hide."""
+    d = gpu_decoders[prec]
+    ids = torch.from_numpy(golden["b2x24_ids"]).cuda()
+    d.set_stage_taps(True)
+    try:
+        wav = d(ids)
+        got = {name: d.read_stage(name) for name in
+               ("embed", "prior_net", "tblock0", "transformers", "backbone", "head_linear")}
+    finally:
+        d.set_stage_taps(False)
+    check_wave(torch.from_numpy(golden["b2x24_wav"]), wav.cpu(), prec, "b2x24 (taps on)")
+    floors = STAGE_SNR[prec]
+    for name, t in got.items():
+        ref = torch.from_numpy(golden[f"b2x24_{name}"])
+        if name in ("embed", "prior_net"):
+            ref = ref.transpose(1, 2)          # (B, C, T) -> (B, T, C)
+        ref = ref.reshape(-1, ref.shape[-1])
+        assert t.shape == ref.shape, (name, t.shape, ref.shape)
+        snr = O.snr_db(ref, t)
+        print(f"[stage] {name} {prec}: SNR {snr:.1f} dB")
+        assert snr >= floors.get(name, floors["default"]), f"{name}: {snr:.1f} dB"
+    with pytest.raises(KeyError):
+        d.read_stage("embed")                  # taps are off again: nothing is kept
+
+
+def test_config4_long_form_vs_oracle(gpu_decoders, state_dict):
+    """BASELINE config 4 (60 s clips, T = 3000: 24 key tiles per attention CTA, the longest overlap-add):
+    one full-length clip against the fp32 oracle end to end, both precisions."""
+    ids = torch.randint(0, 65536, (1, 3000), generator=torch.Generator().manual_seed(4))
+    ref = O.decoder_forward(state_dict, ids)
+    for prec in ("bf16", "fp16"):
+        # decoded inside the full 4 x 3000 batch of the config (row 2), not alone
+        batch = torch.randint(0, 65536, (4, 3000), generator=torch.Generator().manual_seed(44))
+        batch[2] = ids[0]
+        wav = gpu_decoders[prec](batch.cuda()).cpu()
+        check_wave(ref[0], wav[2], prec, "config4 1 x 3000 (row 2 of 4 x 3000)")
+
+
+def test_config3_bucket_vs_oracle(gpu_decoders, state_dict):
+    """BASELINE config 3's unit of work: one length-sorted varlen pack (12 utterances, 100..1000 tokens,
+    built by the same bucketing the sharded run uses); three members (longest, a middle one, shortest)
+    against the fp32 ORACLE -- not against the GPU's own single decode."""
+    from tts_max_b200 import sharding
+
+    g = torch.Generator().manual_seed(2024)
+    lengths = torch.randint(100, 1001, (12,), generator=g).tolist()
+    lengths[3], lengths[7] = 1000, 100
+    utts = [torch.randint(0, 65536, (n,), generator=g) for n in lengths]
+    (bucket,) = sharding.bucket_by_length(range(12), lengths, max_tokens=16384)
+    seqlens = [lengths[i] for i in bucket]
+    offs = [0]
+    for n in seqlens:
+        offs.append(offs[-1] + n)
+    packed_ids = torch.cat([utts[i] for i in bucket])
+    for prec in ("bf16", "fp16"):
+        wav = gpu_decoders[prec].decode_packed_host(packed_ids, seqlens)
+        for k in (0, len(bucket) // 2, len(bucket) - 1):
+            ref = O.decoder_forward(state_dict, utts[bucket[k]].view(1, -1))[0, 0]
+            check_wave(ref, wav[offs[k] * 320:offs[k + 1] * 320], prec, f"config3 pack member {k} (T = {seqlens[k]})")

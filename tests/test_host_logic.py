@@ -119,3 +119,44 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.parametrize("name,hop,ups,ks", [("xcodec2", 320, None, None), ("48k", 160, [3, 2], [7, 6])])
+def test_random_init_matches_reference_statistics(name, hop, ups, ks):
+    """`random_init_state_dict` restates the reference's init DISTRIBUTIONS
+    (decoder_modules.py:403-433, 13-16, 463-464; torch defaults elsewhere). Golden = per-tensor
+    (mean, std, min, max) of the unmodified reference `Decoder(...)` averaged over seeds 0..2
+    (oracle/make_golden_init.py). Same key order, same shapes; mean / std agree statistically, bounded
+    distributions (uniform, constants) agree in their range."""
+    import math
+
+    import numpy as np
+
+    from tts_max_b200.codec import decoder
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_init_stats.npz"))
+    keys = [str(k) for k in g[f"{name}/keys"]]
+    mine = [decoder.random_init_state_dict(hop, seed=s, upsample_factors=ups, kernel_sizes=ks) for s in (10, 11, 12)]
+    assert list(mine[0].keys()) == keys
+    for k in keys:
+        ref_mean, ref_std, ref_min, ref_max = (float(v) for v in g[f"{name}/stats/{k}"])
+        shape = tuple(int(d) for d in g[f"{name}/shape/{k}"])
+        assert tuple(mine[0][k].shape) == shape, k
+        n = math.prod(shape)
+        vals = torch.stack([m[k].double().flatten() for m in mine])
+        mean, std = vals.mean().item(), (vals.std(dim=1).mean().item() if n > 1 else 0.0)
+        lo, hi = vals.min(dim=1).values.mean().item(), vals.max(dim=1).values.mean().item()
+        if ref_std == 0.0 or k.endswith("istft.window") or k.endswith("weight_g"):
+            # constants (norm weights / biases, zero conv biases), the Hann window, and weight_g = ||v||
+            assert abs(mean - ref_mean) <= 2e-2 * max(abs(ref_mean), 1e-12) + 1e-12, k
+            assert abs(std - ref_std) <= 3e-2 * max(ref_std, 1e-12) + 1e-12, k
+            continue
+        # mean of 3 seeds x n samples on both sides: allow 6 standard errors
+        assert abs(mean - ref_mean) <= 6.0 * ref_std * math.sqrt(2.0 / (3 * n)) + 1e-12, (k, mean, ref_mean)
+        assert abs(std - ref_std) <= ref_std * (0.02 + 4.0 / math.sqrt(3 * n)), (k, std, ref_std)
+        uniform = abs(ref_max / ref_std - math.sqrt(3.0)) < 0.1      # U(-b, b): max = b = sqrt(3) std
+        if uniform:
+            assert abs(hi - ref_max) <= 0.03 * ref_max + 2.0 * ref_max / n, (k, hi, ref_max)
+            assert abs(lo - ref_min) <= 0.03 * abs(ref_min) + 2.0 * abs(ref_min) / n, (k, lo, ref_min)
+        # trunc_normal_(std=0.02) with torch's default cut at +-2 (absolute) is an unbounded-looking
+        # normal: its extremes are tail events, only mean / std are compared

@@ -79,8 +79,8 @@ def test_gpu_quantize_vs_golden(qgolden, gpu_decoders, pre):
     dec = gpu_decoders["bf16"]
     hidden = torch.from_numpy(qgolden["hidden"]).cuda()
     code = encoder.FSQQuantizer(dec, pre_bound=bool(pre)).quantize(hidden)
-    assert code.shape == (hidden.shape[0], 1, hidden.shape[2]) and code.dtype == torch.int64
-    ids = code[:, 0, :].cpu()
+    assert code.shape == (hidden.shape[0], 1, hidden.shape[2]) and code.dtype == torch.int32   # FSQ.codes_to_indices
+    ids = code[:, 0, :].cpu().long()
     want = torch.from_numpy(qgolden[f"ids_pre{pre}"])
     clear = off_boundary(torch.from_numpy(qgolden[f"bounded_pre{pre}"]))
     assert clear.float().mean() > 0.99
@@ -89,7 +89,7 @@ def test_gpu_quantize_vs_golden(qgolden, gpu_decoders, pre):
     # the projection itself
     tok = hidden.permute(0, 2, 1).reshape(-1, 2048).contiguous()
     ids2, z = dec.quantize_features(tok, pre_bound=bool(pre), return_projection=True)
-    assert torch.equal(ids2.cpu(), ids.reshape(-1))
+    assert torch.equal(ids2.cpu().long(), ids.reshape(-1))
     np.testing.assert_allclose(z.cpu().numpy(), qgolden["z"].reshape(-1, 8), rtol=0, atol=2e-5)
 
 
@@ -106,7 +106,7 @@ def test_gpu_quantize_round_trip_full_size(gpu_decoders, state_dict):
     g = torch.Generator().manual_seed(99)
     n = 16 * 500
     feats = (torch.randn(n, 2048, generator=g) * 2.0).cuda()
-    ids, z = dec.quantize_features(feats, return_projection=True)
+    ids, z = dec.quantize_features(feats, pre_bound=False, return_projection=True, id_dtype=torch.int64)
     assert ids.min() >= 0 and ids.max() < 65536
     bounded = O.fsq_bound(z.cpu())
     clear = off_boundary(bounded)
@@ -131,14 +131,16 @@ def test_gpu_quantize_round_trip_full_size(gpu_decoders, state_dict):
     assert torch.equal(out.cpu(), ref)
     # batch invariance, ragged tail (n not a multiple of the 4 tokens a warp handles)
     for lo, hi in ((0, 1), (5, 8), (123, 130), (n - 3, n)):
-        assert torch.equal(dec.quantize_features(feats[lo:hi].clone()), ids[lo:hi])
+        assert torch.equal(dec.quantize_features(feats[lo:hi].clone(), pre_bound=False, id_dtype=torch.int64), ids[lo:hi])
 
 
 @pytest.mark.gpu
 def test_gpu_quantize_rejects_bad_input(gpu_decoders):
     dec = gpu_decoders["bf16"]
     with pytest.raises(ValueError):
-        dec.quantize_features(torch.zeros(4, 2048))                     # CPU tensor
+        dec.quantize_features(torch.zeros(4, 2048), pre_bound=False)                     # CPU tensor
     with pytest.raises(ValueError):
-        dec.quantize_features(torch.zeros(4, 2048, device="cuda", dtype=torch.float16))
-    assert dec.quantize_features(torch.zeros(0, 2048, device="cuda")).numel() == 0
+        dec.quantize_features(torch.zeros(4, 2048, device="cuda", dtype=torch.float16), pre_bound=False)
+    assert dec.quantize_features(torch.zeros(0, 2048, device="cuda"), pre_bound=False).numel() == 0
+    with pytest.raises(TypeError):
+        dec.quantize_features(torch.zeros(4, 2048, device="cuda"))   # pre_bound has no default (parity unpinned)

@@ -60,7 +60,7 @@ def test_push_equals_window_decode(gpu_decoders, state_dict, use_graph):
         assert sd.context_tokens == min(ctx_len, (k + 1) * new)
         if k in (0, n_push - 1):   # pin the definition itself on the oracle: first and a steady-state step
             ref = O.decoder_forward(state_dict, window[:1])[:, 0, -new * 320:]
-            assert O.snr_db(ref, out[:1].cpu()) >= 30.0
+            assert O.snr_db(ref, out[:1].cpu()) >= 40.0
     # a new stream after reset() sees no history
     sd.reset()
     first = sd.push(ids[:, :new])
@@ -68,6 +68,38 @@ def test_push_equals_window_decode(gpu_decoders, state_dict, use_graph):
     assert (first - want).abs().max().item() <= 1e-5 * max(1e-3, want.abs().max().item())
     with pytest.raises(ValueError):
         sd.push(ids[:, :new + 1])
+
+
+@pytest.mark.gpu
+def test_graph_survives_reset_and_foreign_decodes(gpu_decoders):
+    """The captured CUDA graph bakes the decoder handle's plan and workspace in. reset() is followed by
+    warm-up pushes of other shapes, and callers may decode unrelated batches (here: a LARGER one, which
+    reallocates the workspace) between steady pushes: every steady push must still equal the eager
+    window decode (the graph is re-captured when the handle's plan generation moved)."""
+    from tts_max_b200.codec import streaming
+
+    d = gpu_decoders["bf16"]
+    n_streams, new, ctx_len = 2, 8, 16
+    g = torch.Generator().manual_seed(99)
+    ids = torch.randint(0, 65536, (n_streams, new * 12), generator=g)
+    other = torch.randint(0, 65536, (5, 211), generator=g).cuda()
+    bigger = torch.randint(0, 65536, (9, 1200), generator=g).cuda()
+    sd = streaming.StreamingDecoder(d, n_streams, new_tokens=new, left_context=ctx_len, use_graph=True)
+
+    def run(n_push, foreign):
+        for k in range(n_push):
+            out = sd.push(ids[:, k * new:(k + 1) * new])
+            lo = max(0, (k + 1) * new - (ctx_len + new))
+            want = d(ids[:, lo:(k + 1) * new].cuda())[:, 0, -new * 320:]
+            assert (out - want).abs().max().item() <= 1e-5 * max(1e-3, want.abs().max().item()), k
+            if foreign and k % 2 == 1:
+                d(other if k % 4 == 1 else bigger)       # another shape on the same decoder
+
+    run(6, foreign=False)     # warm-up, capture, replay
+    sd.reset()
+    run(8, foreign=False)     # warm-up pushes after reset() invalidate the old graph
+    sd.reset()
+    run(12, foreign=True)     # unrelated decodes between steady pushes
 
 
 @pytest.mark.gpu

@@ -10,7 +10,7 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PRECISIONS = {"bf16": 0, "fp16": 1}
 IDS_I32, IDS_I64 = 0, 1
 DT_F32, DT_F16, DT_BF16, DT_F64 = 0, 1, 2, 3
@@ -49,6 +49,11 @@ SIGNATURES = {
     "b200codec_decode_varlen": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_decode_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_take_id_error": (c_int, [c_void_p]),
+    "b200codec_plan_generation": (c_int64, [c_void_p]),
+    "b200codec_set_stage_taps": (c_int, [c_void_p, c_int]),
+    "b200codec_stage_width": (c_int, [c_void_p, c_char_p]),
+    "b200codec_stage_rows": (c_int64, [c_void_p, c_char_p]),
+    "b200codec_read_stage": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
     "b200codec_set_attention_impl": (c_int, [c_int]),
     "b200codec_set_zero_copy_output": (c_int, [c_int]),
     "b200codec_set_gemm_narrow_tiles": (c_int, [c_int]),

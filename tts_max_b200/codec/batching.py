@@ -13,6 +13,7 @@ single-utterance `decode` of the same ids.
 
 from __future__ import annotations
 
+import logging
 import os
 from typing import Iterable, Iterator, Sequence
 
@@ -21,6 +22,8 @@ import torch
 
 from tts_max_b200 import sharding
 from tts_max_b200.codec.decoding import AudioDecoder
+
+_LOG = logging.getLogger(__name__)
 
 
 def extract_speech_ids(speech_tokens_str: Sequence[str]) -> list[int]:
@@ -54,9 +57,30 @@ def decode_completions(
         todo.append(i)
         utts.append(torch.cat([p.detach().to("cpu", torch.int64).reshape(-1), g.detach().to("cpu", torch.int64).reshape(-1)]))
     lengths = [int(u.numel()) for u in utts]
-    for bucket in sharding.bucket_by_length(range(len(utts)), lengths, max_tokens=max_tokens):
-        wavs = audio_decoder.decode_batch([utts[k] for k in bucket])
+    # One bad completion must not fail the others: `_decode_audio` wraps each decode in try/except and
+    # returns zeros((1, 0)) for the one that failed (rewards.py:86-97). Ids are validated per utterance
+    # BEFORE packing, so a bucket never aborts on someone else's out-of-range id.
+    bad = {k for k, u in enumerate(utts) if int(u.min()) < 0 or int(u.max()) > 65535}
+    for k in bad:
+        _LOG.error("Error decoding audio: speech id outside [0, 65535] in completion %d", todo[k])
+        out[todo[k]] = torch.zeros((1, 0))
+    good = [k for k in range(len(utts)) if k not in bad]
+    for bucket in sharding.bucket_by_length(good, lengths, max_tokens=max_tokens):
+        try:
+            wavs = audio_decoder.decode_batch([utts[k] for k in bucket])
+        except Exception as e:  # the reference catches everything per completion
+            _LOG.error("Error decoding a bucket of %d completions (%s); retrying one by one", len(bucket), e)
+            wavs = []
+            for k in bucket:
+                try:
+                    wavs.append(audio_decoder.decode_batch([utts[k]])[0])
+                except Exception as e1:
+                    _LOG.error("Error decoding audio: %s", e1)
+                    wavs.append(None)
         for k, wav in zip(bucket, wavs):
+            if wav is None:
+                out[todo[k]] = torch.zeros((1, 0))
+                continue
             i = todo[k]
             prompt_wav_length = int(prompt_speech_ids[i].numel() / audio_decoder.token_rate * audio_decoder.sample_rate)
             out[i] = wav[:, prompt_wav_length:]

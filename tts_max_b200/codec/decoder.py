@@ -102,9 +102,13 @@ def random_init_state_dict(
     kernel_sizes: Sequence[int] | None = None,
 ) -> "collections.OrderedDict[str, torch.Tensor]":
     """Random initialisation with the reference's distributions (not its RNG stream):
-    Conv1d weight trunc_normal(std=0.02) / bias 0 (decoder_modules.py:13-16, 463-464),
-    Linear = torch default (kaiming_uniform(a=sqrt(5)) -> U(+-1/sqrt(fan_in)) for weight and
-    bias), norm weight 1 / bias 0, `window` = periodic hann (decoder_modules.py:32-33)."""
+    Conv1d weight trunc_normal(std=0.02) / bias 0 inside `Generator` (decoder_modules.py:13-16, 463-464:
+    `self.apply(init_weights)` covers the backbone only), Linear = torch default
+    (kaiming_uniform(a=sqrt(5)) -> U(+-1/sqrt(fan_in)) for weight and bias), norm weight 1 / bias 0,
+    `window` = periodic hann (decoder_modules.py:32-33). The UpSamplerBlock sits outside `Generator`
+    (decoder.py:48-61), so ITS Conv1d / ConvTranspose1d / Linear layers keep torch's defaults
+    (U(+-1/sqrt(fan_in)) for weight and bias). Checked against the reference's own init statistics in
+    tests/test_host_logic.py::test_random_init_matches_reference_statistics."""
     gen = torch.Generator().manual_seed(seed) if seed is not None else None
     out: "collections.OrderedDict[str, torch.Tensor]" = collections.OrderedDict()
     all_shapes = expected_state_dict_shapes(hop_length, DEPTH, upsample_factors, kernel_sizes)
@@ -121,6 +125,11 @@ def random_init_state_dict(
             pending_g[key[: -len("weight_v")] + "weight_g"] = t.reshape(shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
         elif "norm" in key:
             t = torch.ones(shape) if key.endswith("weight") else torch.zeros(shape)
+        elif key.startswith("upsampler.resnet_blocks.") and ("conv" in key):
+            # torch Conv1d default (no init_weights outside Generator): fan_in = Cin * k
+            wshape = shape if len(shape) == 3 else all_shapes[key[: -len("bias")] + "weight"]
+            bound = 1.0 / math.sqrt(wshape[1] * wshape[2])
+            t = (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
         elif len(shape) == 3:  # Conv1d weight
             t = torch.empty(shape)
             torch.nn.init.trunc_normal_(t, std=0.02, generator=gen)
@@ -193,6 +202,7 @@ class Decoder(torch.nn.Module):
         self._host_state: "collections.OrderedDict[str, torch.Tensor]" = random_init_state_dict(
             hop_length, init_seed, self.upsample_factors, self.kernel_sizes)
         self._handle: ctypes.c_void_p | None = None
+        self._pinned_out: torch.Tensor | None = None
         self._device: torch.device = torch.device("cpu")
         self._dirty = True
 
@@ -343,23 +353,29 @@ class Decoder(torch.nn.Module):
         batch, _, length = vq_codes.shape
         if batch == 0 or length == 0:
             raise ValueError(f"decode: empty batch or empty utterance (shape {tuple(vq_codes.shape)})")
-        handle = self._ensure_handle()
         ids = vq_codes.to(self._device).reshape(batch * length).contiguous()
         wavs = self.decode_packed_device(ids, [length] * batch)
         return wavs.view(batch, 1, self.samples_per_token * length)
 
     @torch.no_grad()
-    def decode_packed_device(self, ids: torch.Tensor, seqlens: Sequence[int]) -> torch.Tensor:
+    def decode_packed_device(self, ids: torch.Tensor, seqlens: Sequence[int],
+                             out: torch.Tensor | None = None) -> torch.Tensor:
         """Varlen decode of packed device ids (sum(seqlens),) -> packed device waveform
-        (hop_length * sum(seqlens),); asynchronous on the current stream."""
+        (hop_length * sum(seqlens),); asynchronous on the current stream. `out` (optional): a
+        contiguous float32 device tensor of exactly that many samples to write into (e.g. a slice of a
+        shard-wide PCM buffer that is gathered afterwards)."""
         handle = self._ensure_handle()
         lib = _lib.load()
         total = int(sum(int(t) for t in seqlens))
         if ids.device != self._device or ids.dim() != 1 or ids.numel() != total:
             raise ValueError("ids must be a packed 1-D tensor on the decoder's device matching seqlens")
         id_type = _lib.IDS_I64 if ids.dtype == torch.int64 else _lib.IDS_I32
+        n_out = total * self.samples_per_token
+        if out is not None and (out.device != self._device or out.dtype != torch.float32 or out.numel() != n_out
+                                or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous float32 tensor of hop * sum(seqlens) samples on the decoder's device")
         with torch.cuda.device(self._device):
-            wav = torch.empty(total * self.samples_per_token, dtype=torch.float32, device=self._device)
+            wav = out if out is not None else torch.empty(n_out, dtype=torch.float32, device=self._device)
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(lib.b200codec_decode_varlen(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
                                                    _lib.i32_array(seqlens), len(seqlens),
@@ -379,14 +395,26 @@ class Decoder(torch.nn.Module):
             raise TypeError(f"ids must be int32 or int64, got {ids.dtype}")
         ids = ids.contiguous()
         id_type = _lib.IDS_I64 if ids.dtype == torch.int64 else _lib.IDS_I32
-        if out is None:
-            out = torch.empty(total * self.samples_per_token, dtype=torch.float32, pin_memory=True)
+        n_out = total * self.samples_per_token
+        if out is not None:
+            if out.device.type != "cpu" or out.dtype != torch.float32 or out.numel() != n_out or not out.is_contiguous():
+                raise ValueError("out must be a contiguous float32 CPU tensor of hop * sum(seqlens) samples")
+            dst = out
+        else:
+            # One page-locked staging buffer per decoder (grow-only): the last kernel stores the PCM
+            # straight into it (zero-copy). Callers get a pageable copy, so accumulating results (a
+            # dataset sweep) never pins an unbounded amount of host memory; pass `out=` (ideally a
+            # pinned tensor the caller reuses) to skip the copy.
+            if self._pinned_out is None or self._pinned_out.numel() < n_out:
+                self._pinned_out = None
+                self._pinned_out = torch.empty(n_out + n_out // 4, dtype=torch.float32, pin_memory=True)
+            dst = self._pinned_out[:n_out]
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(lib.b200codec_decode_host(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
                                                  _lib.i32_array(seqlens), len(seqlens),
-                                                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)))
-        return out
+                                                 ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(stream)))
+        return dst if out is not None else dst.clone()
 
     def take_id_error(self) -> bool:
         """True if a device-side decode since the last call saw an id outside [0, 65535]."""
@@ -395,11 +423,15 @@ class Decoder(torch.nn.Module):
         return bool(_lib.load().b200codec_take_id_error(self._handle))
 
     @torch.no_grad()
-    def quantize_features(self, feats: torch.Tensor, pre_bound: bool = False,
-                          return_projection: bool = False):
+    def quantize_features(self, feats: torch.Tensor, *, pre_bound: bool,
+                          return_projection: bool = False, id_dtype: torch.dtype = torch.int32):
         """Encode-direction FSQ with this checkpoint's `quantizer.project_in`: token-major
-        features (n_tokens, 2048) fp32 on the device -> int64 ids (n_tokens,)
-        [+ the (n_tokens, 8) projected values]. See `codec.encoder.FSQQuantizer`."""
+        features (n_tokens, 2048) fp32 on the device -> ids (n_tokens,) [+ the (n_tokens, 8) projected
+        values]. ids are int32 like `FSQ.codes_to_indices` returns them (int64 on request).
+        `pre_bound` has NO default: whether vector-quantize-pytorch 1.17.8 applies `FSQ.bound` to the
+        projected input once more before the layer loop cannot be checked offline (parity unpinned at
+        that library boundary), so the caller must say which release behaviour it wants.
+        See `codec.encoder.FSQQuantizer`."""
         handle = self._ensure_handle()
         lib = _lib.load()
         if feats.device != self._device or feats.dim() != 2 or feats.dtype != torch.float32:
@@ -408,17 +440,43 @@ class Decoder(torch.nn.Module):
             feats = feats.contiguous()
         n = feats.shape[0]
         with torch.cuda.device(self._device):
-            ids = torch.empty(n, dtype=torch.int64, device=self._device)
+            if id_dtype not in (torch.int32, torch.int64):
+                raise TypeError("id_dtype must be torch.int32 or torch.int64")
+            ids = torch.empty(n, dtype=id_dtype, device=self._device)
             z = torch.empty(n, 8, dtype=torch.float32, device=self._device) if return_projection else None
             if n == 0:
                 return (ids, z) if return_projection else ids
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(lib.b200codec_fsq_quantize(
                 handle, ctypes.c_void_p(feats.data_ptr()), int(feats.stride(0)) if n > 1 else feats.shape[1], n,
-                ctypes.c_void_p(ids.data_ptr()), _lib.IDS_I64,
+                ctypes.c_void_p(ids.data_ptr()), _lib.IDS_I64 if id_dtype == torch.int64 else _lib.IDS_I32,
                 ctypes.c_void_p(z.data_ptr()) if z is not None else None, 1 if pre_bound else 0,
                 ctypes.c_void_p(stream)))
         return (ids, z) if return_projection else ids
+
+    def plan_generation(self) -> int:
+        """Changes whenever a decode rebuilt the handle's plan / workspace (a CUDA graph captured from a
+        decode is only valid while this value stays what it was right after capture)."""
+        return 0 if self._handle is None else int(_lib.load().b200codec_plan_generation(self._handle))
+
+    def set_stage_taps(self, on: bool) -> None:
+        """Debug: keep copies of named stage tensors of every decode (see b200codec.h)."""
+        _lib.check(_lib.load().b200codec_set_stage_taps(self._ensure_handle(), 1 if on else 0))
+
+    def read_stage(self, name: str) -> torch.Tensor:
+        """Packed token-major fp32 (rows, width) copy of a tapped stage of the LAST decode."""
+        lib = _lib.load()
+        handle = self._ensure_handle()
+        width = int(lib.b200codec_stage_width(handle, name.encode()))
+        rows = int(lib.b200codec_stage_rows(handle, name.encode()))
+        if width <= 0 or rows < 0:
+            raise KeyError(f"no stage tap named {name!r} (enable set_stage_taps(True) and decode first)")
+        out = torch.empty(rows, width, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(lib.b200codec_read_stage(handle, name.encode(), ctypes.c_void_p(out.data_ptr()),
+                                                out.numel(), ctypes.c_void_p(stream)))
+        return out
 
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_lib.load().b200codec_launch_count(self._handle))

@@ -20,13 +20,19 @@ from tts_max_b200.codec import decoder as decoder_lib
 class FSQQuantizer:
     """`quantize(hidden_states)` with the reference's shapes, backed by b200codec_fsq_quantize."""
 
-    def __init__(self, decoder: decoder_lib.Decoder, pre_bound: bool = False):
+    def __init__(self, decoder: decoder_lib.Decoder, *, pre_bound: bool):
+        """`pre_bound` is REQUIRED: releases of vector-quantize-pytorch differ in whether
+        `ResidualFSQ.forward` applies `layers[0].bound` to the projected input before the layer loop,
+        the pinned 1.17.8 wheel is not available offline, and the two variants give different ids for
+        most inputs (bound(bound(z)) != bound(z)). Encode parity is therefore UNVERIFIED at that library
+        boundary; pass what the wheel you deploy against does."""
         self._decoder = decoder
-        self._pre_bound = pre_bound
+        self._pre_bound = bool(pre_bound)
 
     @torch.no_grad()
     def quantize(self, hidden_states: torch.Tensor) -> torch.Tensor:
-        """(B, 2048, T) float32 -> (B, 1, T) int64 FSQ ids in [0, 65536)."""
+        """(B, 2048, T) float32 -> (B, 1, T) int32 FSQ ids in [0, 65536) (`FSQ.codes_to_indices`
+        returns int32)."""
         if hidden_states.dim() != 3:
             raise ValueError("hidden_states must be (batch, channels, frames)")
         b, c, t = hidden_states.shape

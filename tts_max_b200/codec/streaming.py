@@ -58,11 +58,13 @@ class StreamingDecoder:
         self._filled = 0  # valid context tokens (identical for all streams: they advance together)
         self._graph: torch.cuda.CUDAGraph | None = None
         self._graph_wav: torch.Tensor | None = None
-        self._steady_steps = 0
+        self._graph_generation = -1  # Decoder.plan_generation() right after capture
 
     # ------------------------------------------------------------------------------------------
     def reset(self) -> None:
-        """Start new streams (drops the token history; a captured graph stays valid)."""
+        """Start new streams (drops the token history). The warm-up pushes that follow decode other
+        shapes on the same decoder, which rebuilds its plan: the captured graph is detected as stale
+        (plan generation) and re-captured at the first steady push."""
         self._filled = 0
         self._window.zero_()
 
@@ -98,19 +100,23 @@ class StreamingDecoder:
         seqlens = [win] * self.n_streams
         if not self._use_graph:
             return self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
-        if self._graph is None:
-            self._steady_steps += 1
-            if self._steady_steps < 2:
-                # first steady step runs eagerly: plan, workspace and tensor maps of this shape get built
-                return self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
-            stream = torch.cuda.Stream(device=self._device)
-            stream.wait_stream(torch.cuda.current_stream(self._device))
-            with torch.cuda.stream(stream):
-                self._dec.decode_packed_device(self._window.view(-1), seqlens)
-            torch.cuda.current_stream(self._device).wait_stream(stream)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                self._graph_wav = self._dec.decode_packed_device(self._window.view(-1), seqlens)
-            self._graph = graph
-        self._graph.replay()
-        return self._graph_wav.view(self.n_streams, -1)
+        # The graph bakes in the decoder handle's plan / workspace / statistics pointers and the plan
+        # CONTENTS. Any decode of another shape on this decoder (a stream's own warm-up pushes after
+        # reset(), or an unrelated decode between pushes) rewrites or reallocates them, so the graph is
+        # replayed only while the handle's plan generation is the one seen right after capture.
+        if self._graph is not None and self._dec.plan_generation() == self._graph_generation:
+            self._graph.replay()
+            return self._graph_wav.view(self.n_streams, -1)
+        self._graph = None
+        # eager decode of this push: the result, and the plan / workspace / tensor maps of this shape
+        wav = self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
+        # capture for the NEXT push (the capture itself executes nothing)
+        stream = torch.cuda.Stream(device=self._device)
+        stream.wait_stream(torch.cuda.current_stream(self._device))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            self._graph_wav = self._dec.decode_packed_device(self._window.view(-1), seqlens)
+        torch.cuda.current_stream(self._device).wait_stream(stream)
+        self._graph = graph
+        self._graph_generation = self._dec.plan_generation()
+        return wav

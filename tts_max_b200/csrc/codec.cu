@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -174,6 +175,25 @@ struct B200Codec {
 
     size_t l2_persist_bytes = 0;  // persisting-L2 carve-out granted at create (0 = unsupported)
     size_t l2_window_max = 0;
+
+    // Debug taps (b200codec_set_stage_taps): device copies of named stage tensors of the LAST decode,
+    // in the padded row space they were computed in (b200codec_read_stage compacts them to token rows).
+    struct StageTap {
+        DevBuf buf;
+        int width = 0;      // logical columns
+        int ld = 0;         // elements per row as stored
+        int elem = 4;       // 4: fp32, 2: operand dtype
+        int space = 0;      // 0: plan 0 (token rate), i > 0: row space after upsampler stage i - 1
+        bool valid = false;
+    };
+    bool taps_on = false;
+    std::map<std::string, StageTap> taps;
+    // One decode at a time per handle: plan, workspace, statistics and staging buffers are single
+    // instances that a decode rewrites and may reallocate (see b200codec.h "Threading").
+    std::mutex mu;
+    // bumped whenever the plan, the workspace or the statistics buffer is rebuilt or reallocated: a
+    // CUDA graph captured from a decode bakes those pointers and contents in (b200codec_plan_generation)
+    int64_t generation = 0;
 
     int64_t launches = 0;
     bool profiling = false;
@@ -371,6 +391,7 @@ int build_plan(B200Codec* h, const int32_t* seqlens, int n_utts, int gap, cudaSt
     bool same = h->plan_gap == gap && static_cast<int>(h->plan_key.size()) == n_utts &&
                 std::memcmp(h->plan_key.data(), seqlens, sizeof(int32_t) * n_utts) == 0;
     if (same) return 0;
+    h->generation++;
     PlanLayout L;
     if (plan_layout(seqlens, n_utts, gap, &L)) return 1;
     if (L.total_bytes > h->plan_host_bytes) {
@@ -458,6 +479,7 @@ int ensure_workspace(B200Codec* h, int rows) {
         }
         if (h->n_up > 0) total += al(Rlast * C * es);
     }
+    h->generation++;
     h->ws.release();
     h->ws_rows = 0;
     if (h->ws.ensure(total)) return 1;
@@ -661,6 +683,9 @@ int resnet_block(B200Codec* h, const ResBlockW& w, int stats_slot, cudaStream_t 
     return resnet_block_ex(h, cx, w, stats_slot, s, nf, gn1_done, next_gn);
 }
 
+int tap_stage(B200Codec* h, const char* name, const void* src, int elem, int width, int ld, int rows, int space,
+              cudaStream_t s);
+
 // UpSamplerBlock.forward (upsampler.py:62-69): per stage, ConvTranspose1d as `stride` row-shifted convs
 // (one per output phase, written with a row stride of `stride`), then a ResnetBlock; finally
 // out_proj + swish. Input: LayerNorm output h->an (halo rows zero); output: h->u_fin.
@@ -695,10 +720,13 @@ int upsample_path(B200Codec* h, cudaStream_t s) {
                 RUN(launch_gemm(c, s));
             }
         }
+        const std::string tag = std::to_string(i);
+        if (tap_stage(h, ("up" + tag).c_str(), h->u_x[i], 4, st.Cout, st.Cout, rs_out.rows, i + 1, s)) return 1;
         NormFuse nf;
         nf.out16 = h->u_a16[i];  // operand copy of the block output: input of the next stage / out_proj
         ResCtx cx{&rs_out, st.Cout, h->u_x[i], h->u_h[i], h->u_an[i], true};
         if (resnet_block_ex(h, cx, st.res, 8 + 2 * i, s, nf)) return 1;
+        if (tap_stage(h, ("res" + tag).c_str(), h->u_x[i], 4, st.Cout, st.Cout, rs_out.rows, i + 1, s)) return 1;
         cur = h->u_a16[i];
         rs_in = &rs_out;
     }
@@ -723,17 +751,24 @@ int upsample_path(B200Codec* h, cudaStream_t s) {
         c.act = kActSilu;  // nonlinearity(out_proj(x)) (upsampler.py:69)
         RUN(launch_gemm(c, s));
     }
+    if (tap_stage(h, "upsampled", h->u_fin, static_cast<int>(operand_bytes(prec)), h->C, h->C, rs_in->rows, h->n_up, s))
+        return 1;
     return 0;
 }
 
 // The fp32 residual stream x ([rows, 1024]) is re-read by every residual epilogue and GroupNorm after
 // ~150 MB of other activations have gone through L2; pin it with a persisting access-policy window
 // on the caller's stream for the duration of the decode (restored afterwards).
-void set_l2_window(B200Codec* h, cudaStream_t s, bool on) {
+void set_l2_window(B200Codec* h, cudaStream_t s, bool on, cudaStreamAttrValue* saved) {
     if (h->l2_persist_bytes == 0) return;
     cudaStreamAttrValue attr;
     std::memset(&attr, 0, sizeof(attr));
     if (on) {
+        // the caller's own window (if any) comes back after the decode
+        if (cudaStreamGetAttribute(s, cudaStreamAttributeAccessPolicyWindow, saved) != cudaSuccess) {
+            (void)cudaGetLastError();
+            std::memset(saved, 0, sizeof(*saved));
+        }
         size_t bytes = static_cast<size_t>(h->rs.rows) * h->C * sizeof(float);
         if (bytes > h->l2_window_max) bytes = h->l2_window_max;
         attr.accessPolicyWindow.base_ptr = h->x;
@@ -743,19 +778,35 @@ void set_l2_window(B200Codec* h, cudaStream_t s, bool on) {
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     } else {
-        attr.accessPolicyWindow.num_bytes = 0;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        attr = *saved;
     }
     cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
 int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s);
 
+// debug tap: keep a device copy of a stage tensor (whole padded row space) for b200codec_read_stage
+int tap_stage(B200Codec* h, const char* name, const void* src, int elem, int width, int ld, int rows, int space,
+              cudaStream_t s) {
+    if (!h->taps_on) return 0;
+    B200Codec::StageTap& t = h->taps[name];
+    const size_t bytes = static_cast<size_t>(rows) * ld * elem;
+    if (t.buf.ensure(bytes)) return 1;
+    B200_CUDA_OK(cudaMemcpyAsync(t.buf.p, src, bytes, cudaMemcpyDeviceToDevice, s));
+    t.width = width;
+    t.ld = ld;
+    t.elem = elem;
+    t.space = space;
+    t.valid = true;
+    return 0;
+}
+
 int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s) {
-    set_l2_window(h, s, true);
+    cudaStreamAttrValue saved;
+    std::memset(&saved, 0, sizeof(saved));
+    set_l2_window(h, s, true, &saved);
     const int rc = forward_impl(h, ids_dev, id_type, wav_dev, s);
-    set_l2_window(h, s, false);
+    set_l2_window(h, s, false, &saved);
     return rc;
 }
 
@@ -820,8 +871,10 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
             consume.ss_in_scale = 64.f;
         }
     }
+    if (tap_stage(h, "embed", h->x, 4, C, C, rs.rows, 0, s)) return 1;  // backbone.embed output
     if (resnet_block(h, h->res[0], 0, s, NormFuse(), gn0_done, gn_slot(2))) return 1;
     if (resnet_block(h, h->res[1], 2, s, produce, gn_fused, nullptr)) return 1;
+    if (tap_stage(h, "prior_net", h->x, 4, C, C, rs.rows, 0, s)) return 1;
     for (int l = 0; l < h->L; ++l) {
         const LayerW& w = h->layers[l];
         const bool last = l + 1 == h->L;
@@ -861,7 +914,9 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
             }
             RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s, f2));
         }
+        if (l == 0 && tap_stage(h, "tblock0", h->x, 4, C, C, rs.rows, 0, s)) return 1;
     }
+    if (tap_stage(h, "transformers", h->x, 4, C, C, rs.rows, 0, s)) return 1;
     if (resnet_block(h, h->res[2], 4, s, NormFuse(), gn_fused && h->L > 0, gn_slot(6))) return 1;
     if (resnet_block(h, h->res[3], 6, s, NormFuse(), gn_fused, nullptr)) return 1;
     {
@@ -871,6 +926,8 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
                              h->m("decoder.backbone.final_layer_norm.bias"), rs.rows, C, 1e-6f,
                              h->an, s, h->n_up > 0 ? rs.row_valid : nullptr));
     }
+    // VocosBackbone.forward output (final_layer_norm), stored in the operand dtype
+    if (tap_stage(h, "backbone", h->an, static_cast<int>(operand_bytes(prec)), C, C, rs.rows, 0, s)) return 1;
     const RowSpace& rs_last = h->n_up > 0 ? h->rs_up[h->n_up - 1] : rs;
     const void* head_in = h->an;
     if (h->n_up > 0) {
@@ -898,6 +955,7 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
         c.act = kActNone;
         RUN(launch_gemm(c, s));
     }
+    if (tap_stage(h, "head_linear", h->ho, 4, h->n_fft + 2, h->head_ld, rs_last.rows, h->n_up, s)) return 1;
     {
         Stage t(h, "istft", s);
         IstftTables tab;
@@ -1372,8 +1430,8 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     return 0;
 }
 
-int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
-                            const int32_t* seqlens_host, int n_utts, float* wav_dev, void* stream) {
+static int decode_varlen_locked(B200Codec* h, const void* ids_dev, int id_type,
+                                const int32_t* seqlens_host, int n_utts, float* wav_dev, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (prepare(h, seqlens_host, n_utts, s)) return 1;
     B200_CHECK(ids_dev && wav_dev, "decode: null device buffer");
@@ -1382,6 +1440,7 @@ int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
     const size_t need = sizeof(double) * h->gn_slots * static_cast<size_t>(n_utts) * 64 +
                         sizeof(float2) * h->gn_slots * static_cast<size_t>(n_utts) * 32;
     if (h->gn_stats_bytes < need) {
+        h->generation++;
         if (h->gn_stats) B200_CUDA_OK(cudaFree(h->gn_stats));
         h->gn_stats = nullptr;
         h->gn_stats_bytes = 0;
@@ -1394,6 +1453,13 @@ int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
         collect_timers(h);
     }
     return rc;
+}
+
+int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
+                            const int32_t* seqlens_host, int n_utts, float* wav_dev, void* stream) {
+    B200_CHECK(h != nullptr, "null handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    return decode_varlen_locked(h, ids_dev, id_type, seqlens_host, n_utts, wav_dev, stream);
 }
 
 int b200codec_take_id_error(B200Codec* h) {
@@ -1414,6 +1480,7 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
         toks += seqlens_host[u];
     }
     if (check_ids_host(ids_host, id_type, toks)) return 1;
+    std::lock_guard<std::mutex> lock(h->mu);
     B200_CUDA_OK(cudaSetDevice(h->cfg.device));
     const size_t id_bytes = static_cast<size_t>(toks) * (id_type == B200CODEC_IDS_I64 ? 8 : 4);
     const size_t wav_bytes = static_cast<size_t>(toks) * h->hop * h->total_up * sizeof(float);
@@ -1431,10 +1498,10 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
             (void)cudaGetLastError();  // pageable memory: not an error, take the staged path
     }
     if (wav_mapped != nullptr) {
-        if (b200codec_decode_varlen(h, h->io_ids.p, id_type, seqlens_host, n_utts, wav_mapped, s)) return 1;
+        if (decode_varlen_locked(h, h->io_ids.p, id_type, seqlens_host, n_utts, wav_mapped, s)) return 1;
     } else {
         if (h->io_wav.ensure(wav_bytes)) return 1;
-        if (b200codec_decode_varlen(h, h->io_ids.p, id_type, seqlens_host, n_utts, h->io_wav.as<float>(), s))
+        if (decode_varlen_locked(h, h->io_ids.p, id_type, seqlens_host, n_utts, h->io_wav.as<float>(), s))
             return 1;
         B200_CUDA_OK(cudaMemcpyAsync(wav_host, h->io_wav.p, wav_bytes, cudaMemcpyDeviceToHost, s));
     }
@@ -1445,6 +1512,77 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
 int b200codec_samples_per_token(const B200Codec* h) { return h ? h->hop * h->total_up : 0; }
 
 int64_t b200codec_launch_count(const B200Codec* h) { return h ? h->launches : 0; }
+
+int64_t b200codec_plan_generation(const B200Codec* h) { return h ? h->generation : 0; }
+
+int b200codec_set_stage_taps(B200Codec* h, int on) {
+    B200_CHECK(h != nullptr, "null handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->taps_on = on != 0;
+    if (!h->taps_on) {
+        for (auto& kv : h->taps) kv.second.buf.release();
+        h->taps.clear();
+    }
+    return 0;
+}
+
+int b200codec_stage_width(B200Codec* h, const char* name) {
+    if (!h || !name) return -1;
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->taps.find(name);
+    return it == h->taps.end() || !it->second.valid ? -1 : it->second.width;
+}
+
+int64_t b200codec_stage_rows(B200Codec* h, const char* name) {
+    if (!h || !name) return -1;
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->taps.find(name);
+    if (it == h->taps.end() || !it->second.valid) return -1;
+    int64_t factor = 1, toks = 0;
+    for (int i = 0; i < it->second.space; ++i) factor *= h->up_f[i];
+    for (int32_t T : h->plan_key) toks += static_cast<int64_t>(T) * factor;
+    return toks;
+}
+
+int b200codec_read_stage(B200Codec* h, const char* name, float* host_out, size_t n_elems, void* stream) {
+    B200_CHECK(h && name && host_out, "read_stage: null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->taps.find(name);
+    B200_CHECK(it != h->taps.end() && it->second.valid,
+               "read_stage: no tap named \"%s\" (enable b200codec_set_stage_taps, then decode)", name);
+    const B200Codec::StageTap& t = it->second;
+    int factor = 1;
+    for (int i = 0; i < t.space; ++i) factor *= h->up_f[i];
+    int64_t toks = 0;
+    for (int32_t T : h->plan_key) toks += static_cast<int64_t>(T) * factor;
+    B200_CHECK(static_cast<size_t>(toks) * t.width == n_elems, "read_stage %s: expected %lld x %d elements, got %zu",
+               name, (long long)toks, t.width, n_elems);
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    size_t rows = 0;
+    for (size_t u = 0; u < h->plan_key.size(); ++u)
+        rows += static_cast<size_t>(h->plan_key[u]) * factor + (u + 1 < h->plan_key.size() ? kGap * factor : 0);
+    std::vector<uint8_t> raw(rows * t.ld * t.elem);
+    B200_CUDA_OK(cudaMemcpy(raw.data(), t.buf.p, raw.size(), cudaMemcpyDeviceToHost));
+    const int prec = h->cfg.precision;
+    size_t r = 0, o = 0;
+    for (size_t u = 0; u < h->plan_key.size(); ++u) {
+        const size_t T = static_cast<size_t>(h->plan_key[u]) * factor;
+        for (size_t k = 0; k < T; ++k, ++r) {
+            const uint8_t* src = raw.data() + r * t.ld * t.elem;
+            for (int c = 0; c < t.width; ++c) {
+                float v;
+                if (t.elem == 4) v = reinterpret_cast<const float*>(src)[c];
+                else if (prec == kPrecBf16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[c]);
+                else v = __half2float(reinterpret_cast<const __half*>(src)[c]);
+                host_out[o++] = v;
+            }
+        }
+        r += static_cast<size_t>(kGap) * factor;
+    }
+    return 0;
+}
 
 int b200codec_set_attention_impl(int impl) {
     B200_CHECK(impl == 0 || impl == 1, "attention impl must be 0 (tcgen05) or 1 (mma.sync)");

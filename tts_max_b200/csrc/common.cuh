@@ -177,7 +177,7 @@ struct Half16<__half> {
     }
 };
 
-// tcgen05 instruction-descriptor operand format codes (kind::f16 / kind::tf32)
+// tcgen05 instruction-descriptor operand format codes (kind::f16)
 template <typename T>
 struct UmmaFmt;
 template <>
@@ -187,10 +187,6 @@ struct UmmaFmt<__half> {
 template <>
 struct UmmaFmt<__nv_bfloat16> {
     static constexpr uint32_t value = 1;
-};
-template <>
-struct UmmaFmt<float> {
-    static constexpr uint32_t value = 2;
 };
 
 // ---------------------------------------------------------------------------
@@ -336,19 +332,6 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
         : "memory");
 }
 
-// kind::tf32 : fp32 storage in smem, 10-bit mantissa multiply, fp32 accumulate.
-__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                             uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, two 16-bit K elements
 // per 32-bit column), e.g. the softmax probabilities of attention.
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
@@ -430,7 +413,7 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor (kind::f16 / kind::tf32), K-major A and B, fp32 accumulate:
+// Instruction descriptor (kind::f16), K-major A and B, fp32 accumulate:
 //   [4,6) D format (1 = f32)   [7,10) A format   [10,13) B format
 //   [15] A major (0 = K)       [16] B major (0 = K)
 //   [17,23) N >> 3             [24,29) M >> 4

@@ -103,8 +103,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     using SM = GemmSmem<BLOCK_N, kStages>;
     constexpr int BLOCK_K = 128 / sizeof(InT);   // elements per 128-byte swizzle row
-    constexpr int UMMA_K = 32 / sizeof(InT);     // 16 for bf16/fp16, 8 for tf32
-    constexpr bool kIsTf32 = sizeof(InT) == 4;
+    constexpr int UMMA_K = 32 / sizeof(InT);     // 16 for bf16 / fp16
+    static_assert(sizeof(InT) == 2, "operands are bf16 or fp16");
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
@@ -197,12 +197,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 32 bytes (= UMMA_K elements) inside the swizzle span: +2 in >>4 units
-                        if constexpr (kIsTf32)
-                            umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                         (kb | k) != 0);
-                        else
-                            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                        (kb | k) != 0);
+                        umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
                     if (++stage == kStages) {

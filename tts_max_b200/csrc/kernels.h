@@ -9,9 +9,8 @@ namespace b200 {
 // precision codes == enum B200CodecPrecision
 constexpr int kPrecBf16 = 0;
 constexpr int kPrecFp16 = 1;
-constexpr int kPrecTf32 = 2;
 
-inline size_t operand_bytes(int precision) { return precision == kPrecTf32 ? 4 : 2; }
+inline size_t operand_bytes(int /*precision*/) { return 2; }
 
 // The padded row space all activations live in: utterance u occupies rows
 // [utt_row0[u], utt_row0[u] + utt_len[u]); `gap` rows that stay zero in every conv
@@ -100,7 +99,7 @@ struct GemmCall {
     int taps;
     int tap_pad = -1;    // A row = m + tap - tap_pad; -1 -> taps / 2 ("same" conv)
     void* out;
-    int out_fp32;        // 1 -> fp32 output, 0 -> operand dtype (tf32 mode: always fp32 storage)
+    int out_fp32;        // 1 -> fp32 output, 0 -> operand dtype
     int ldc;
     int n_store;         // multiple of 32, <= ldc; columns >= N get bias only (zeros)
     const float* bias;

@@ -62,28 +62,48 @@ def bucket_by_length(indices: Sequence[int], lengths: Sequence[int], max_tokens:
     return buckets
 
 
+def gather_packed(flat: torch.Tensor, gathered: list[torch.Tensor] | None, dst: int = 0) -> None:
+    """ONE `dist.gather` of equal-sized packed PCM buffers: `gathered` (a list of world_size tensors shaped
+    like `flat`) is filled on `dst` and must be None elsewhere. Only `dst` receives data."""
+    import torch.distributed as dist
+
+    dist.gather(flat, gathered if dist.get_rank() == dst else None, dst=dst)
+
+
 def gather_waveforms(local: dict[int, torch.Tensor], lengths: Sequence[int], hop: int, rank: int,
-                     world_size: int, dst: int = 0, device: torch.device | str | None = None):
-    """The only collective of the path: gathers every rank's waveforms on `dst`. `local` maps
-    utterance index -> (hop * T,) float32 tensor. Returns {index: tensor} on `dst`, None elsewhere.
-    Uses one all_gather of a padded flat buffer (NCCL over NVLink on GPUs, gloo on CPU)."""
+                     world_size: int, dst: int = 0, device: torch.device | str | None = None,
+                     owner_lists: Sequence[Sequence[int]] | None = None):
+    """The only collective of the path: the final gather of every rank's waveforms on `dst`
+    (BASELINE north star: "no collective on the hot path beyond a final gather of waveforms").
+    `local` maps utterance index -> (hop * T,) float32 tensor. Returns {index: tensor} on `dst`, None
+    elsewhere.
+
+    ONE `dist.gather` of each rank's packed PCM (ncclGather over NVLink on GPUs, gloo on CPU): only
+    `dst` receives data -- config 3's ~7 GB of PCM lands once, not on every rank. The partition is a
+    pure function of `lengths` (`partition_utterances`), so every rank can compute who owns what:
+    pass `owner_lists` to skip the small `all_gather_object` of the index lists."""
     import torch.distributed as dist
 
     if world_size == 1:
         return dict(local)
-    owner_lists: list[list[int]] = [None] * world_size  # type: ignore[list-item]
-    dist.all_gather_object(owner_lists, sorted(local.keys()))
+    if owner_lists is None:
+        gathered_owned: list[list[int]] = [None] * world_size  # type: ignore[list-item]
+        dist.all_gather_object(gathered_owned, sorted(local.keys()))
+        owner_lists = gathered_owned
+    owner_lists = [sorted(int(i) for i in owned) for owned in owner_lists]
+    if sorted(local.keys()) != owner_lists[rank]:
+        raise ValueError("gather_waveforms: `local` does not hold exactly this rank's utterances")
     totals = [sum(int(lengths[i]) for i in owned) * hop for owned in owner_lists]
-    width = max(max(totals), 1)
+    width = max(max(totals), 1)  # gather needs equal-sized tensors: pad to the largest shard
     dev = torch.device(device) if device is not None else (next(iter(local.values())).device if local else torch.device("cpu"))
     flat = torch.zeros(width, dtype=torch.float32, device=dev)
     off = 0
-    for i in sorted(local.keys()):
+    for i in owner_lists[rank]:
         n = int(lengths[i]) * hop
         flat[off:off + n] = local[i].reshape(-1).to(dev)
         off += n
-    gathered = [torch.empty_like(flat) for _ in range(world_size)]
-    dist.all_gather(gathered, flat)
+    gathered = [torch.empty_like(flat) for _ in range(world_size)] if rank == dst else None
+    gather_packed(flat, gathered, dst=dst)
     if rank != dst:
         return None
     out: dict[int, torch.Tensor] = {}
