@@ -169,6 +169,11 @@ int b200codec_set_frontend_fold(int mode);
  * times as many. Every output element sees the same K order, so results are bit-identical. A/B switch. */
 int b200codec_set_gemm_narrow_tiles(int on);
 
+/* Output hops per ISTFT CTA: 12 (8 warps, two CTAs per SM) or 28 (16 warps, one CTA per SM, less halo
+ * recomputation: a tile of H hops transforms H + 4 frames); 0 (default) picks 28 when that still gives every
+ * SM a CTA. Same samples either way. A/B switch. */
+int b200codec_set_istft_tile(int hops);
+
 /* decode_host with a PINNED output buffer lets the last kernel store the PCM straight into host
  * memory (default on; pageable buffers always take the staged device buffer + copy). A/B switch. */
 int b200codec_set_zero_copy_output(int on);

@@ -167,6 +167,7 @@ struct B200Codec {
     size_t plan_host_bytes = 0;
     std::vector<int32_t> plan_key;
     int plan_gap = -1;
+    int plan_istft_mode = -1;
     RowSpace rs, rs_up[kMaxUp];
     // io staging for decode_host
     DevBuf io_ids, io_wav;
@@ -290,12 +291,21 @@ struct PlanLayout {
     int64_t toks = 0;
     int max_len = 0;
     int64_t n_attn = 0, n_attn128 = 0, n_istft = 0;
+    int istft_hops = 12;
     size_t off_row_tok, off_row_utt, off_u0, off_ul, off_ut, off_attn, off_attn128, off_istft, off_valid;
     size_t total_bytes = 0;
 };
 
 int plan_layout(const int32_t* seqlens, int n_utts, int gap, PlanLayout* L) {
     B200_CHECK(n_utts > 0, "decode: empty batch (no utterances)");
+    // ISTFT tile: 28 output hops (16 warps, 32 frames: 1.14x halo recomputation) once that still gives every
+    // SM a CTA, else 12 hops (8 warps, 1.33x) so that short batches spread over more SMs
+    L->istft_hops = g_istft_hops;
+    if (L->istft_hops == 0) {
+        int64_t tiles28 = 0;
+        for (int u = 0; u < n_utts; ++u) tiles28 += (seqlens[u] + 27) / 28;
+        L->istft_hops = tiles28 >= kNumSMs ? 28 : 12;
+    }
     int64_t rows = 0;
     for (int u = 0; u < n_utts; ++u) {
         const int T = seqlens[u];
@@ -306,7 +316,7 @@ int plan_layout(const int32_t* seqlens, int n_utts, int gap, PlanLayout* L) {
         L->max_len = T > L->max_len ? T : L->max_len;
         L->n_attn += (T + kAttnBlockQ - 1) / kAttnBlockQ;
         L->n_attn128 += (T + 127) / 128;
-        L->n_istft += (T + kIstftOutHops - 1) / kIstftOutHops;
+        L->n_istft += (T + L->istft_hops - 1) / L->istft_hops;
     }
     B200_CHECK(rows < (1 << 30), "decode: batch too large (%lld rows)", (long long)rows);
     const size_t R = static_cast<size_t>(rows);
@@ -351,7 +361,7 @@ void plan_fill(const PlanLayout& L, const int32_t* seqlens, int gap, void* host)
             int32_t* w = hp + L.off_attn128 + 4 * ia2++;
             w[0] = static_cast<int32_t>(r); w[1] = T; w[2] = q0; w[3] = 0;
         }
-        for (int b0 = 0; b0 < T; b0 += kIstftOutHops) {
+        for (int b0 = 0; b0 < T; b0 += L.istft_hops) {
             int32_t* w = hp + L.off_istft + 4 * ii++;
             w[0] = u; w[1] = b0; w[2] = 0; w[3] = 0;
         }
@@ -383,12 +393,13 @@ void plan_bind(const PlanLayout& L, const void* dev, RowSpace* rs) {
     rs->n_attn128_work = static_cast<int>(L.n_attn128);
     rs->istft_work = reinterpret_cast<const int4*>(dp + L.off_istft);
     rs->n_istft_work = static_cast<int>(L.n_istft);
+    rs->istft_hops = L.istft_hops;
     rs->row_valid = reinterpret_cast<const uint8_t*>(dp + L.off_valid);
 }
 
 int build_plan(B200Codec* h, const int32_t* seqlens, int n_utts, int gap, cudaStream_t stream) {
     B200_CHECK(n_utts > 0, "decode: empty batch (no utterances)");
-    bool same = h->plan_gap == gap && static_cast<int>(h->plan_key.size()) == n_utts &&
+    bool same = h->plan_gap == gap && h->plan_istft_mode == g_istft_hops && static_cast<int>(h->plan_key.size()) == n_utts &&
                 std::memcmp(h->plan_key.data(), seqlens, sizeof(int32_t) * n_utts) == 0;
     if (same) return 0;
     h->generation++;
@@ -433,6 +444,7 @@ int build_plan(B200Codec* h, const int32_t* seqlens, int n_utts, int gap, cudaSt
     }
     h->plan_key.assign(seqlens, seqlens + n_utts);
     h->plan_gap = gap;
+    h->plan_istft_mode = g_istft_hops;
     return 0;
 }
 
@@ -1415,11 +1427,8 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     B200_CUDA_OK(cudaMemcpyAsync(h->head_bias_pad, h->m("decoder.head.out.bias"),
                                  (h->n_fft + 2) * sizeof(float), cudaMemcpyDeviceToDevice, s));
     {
-        std::vector<float2> tw(h->n_fft);
-        for (int i = 0; i < h->n_fft; ++i) {
-            const double a = 2.0 * M_PI * i / h->n_fft;
-            tw[i] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
-        }
+        std::vector<float2> tw(istft_table_words(h->hop));
+        istft_fill_tables(h->hop, tw.data());
         if (!h->twiddle) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->twiddle), tw.size() * sizeof(float2)));
         B200_CUDA_OK(cudaMemcpy(h->twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }
@@ -1594,6 +1603,12 @@ int b200codec_set_frontend_fold(int mode) {
     B200_CHECK(mode >= 0 && mode <= 2, "front-end mode must be 0 (lookup + conv7 GEMM), 1 (folded, tensor cores) "
                                        "or 2 (folded, fp32 FMA kernel)");
     g_frontend_fold = mode;
+    return 0;
+}
+
+int b200codec_set_istft_tile(int hops) {
+    B200_CHECK(hops == 0 || hops == 12 || hops == 28, "istft tile must be 0 (auto), 12 (8 warps, 2 CTAs per SM) or 28 (16 warps) output hops");
+    g_istft_hops = hops;
     return 0;
 }
 

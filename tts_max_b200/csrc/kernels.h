@@ -32,10 +32,12 @@ struct RowSpace {
     int n_attn128_work = 0;
     const int4* istft_work = nullptr;    // [n_istft_work] {utt, b0, 0, 0}
     int n_istft_work = 0;
+    int istft_hops = 12;                 // output hops per ISTFT work item
 };
 
 constexpr int kAttnBlockQ = 64;     // query rows per attention CTA
-constexpr int kIstftOutHops = 12;   // output hops per ISTFT CTA (+4 halo frames)
+// output hops per ISTFT CTA (+4 halo frames): 12 (8 warps, 2 CTAs per SM) or 28 (16 warps, 1 CTA per SM)
+extern int g_istft_hops;
 
 // ---- fsq.cu ----
 // out_prec: -1 -> fp32 output, else operand dtype of that precision.
@@ -81,9 +83,11 @@ int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int hea
 
 // ---- istft.cu ----
 struct IstftTables {
-    const float2* twiddle = nullptr;  // [n_fft] exp(+2*pi*i*m/n_fft)
+    const float2* twiddle = nullptr;  // istft_table_words(hop) float2, filled by istft_fill_tables(hop, ...)
     const float* window = nullptr;    // [n_fft] from the checkpoint (decoder.head.istft.window)
 };
+int istft_table_words(int hop);
+void istft_fill_tables(int hop, float2* host);
 int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTables& tab,
                  int hop, float* wav, cudaStream_t stream);
 
