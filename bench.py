@@ -373,6 +373,9 @@ def run_ours(args):
     if args.no_pdl:
         from tts_max_b200 import _lib
         _lib.check(_lib.load().b200codec_set_pdl(0))
+    if args.chain:
+        from tts_max_b200 import _lib
+        _lib.check(_lib.load().b200codec_set_gemm_chain(1))
     if args.istft_tile:
         from tts_max_b200 import _lib
         _lib.check(_lib.load().b200codec_set_istft_tile(args.istft_tile))
@@ -472,7 +475,9 @@ def run_ours(args):
         stage_ms_in_step = {k: v / fenced_total * ms_per_step for k, v in stage_ms.items()}
         gemm_share = sum(v for k, v in stage_ms.items() if k.endswith("_gemm")) / fenced_total
         gemm_ms = gemm_share * ms_per_step
-        n_gemm = 1 + 8 + 12 * 4 + 1  # folded front end (K = 128), 8 conv3, 48 transformer linears, head
+        # GEMM launches = all launches minus 12 attention, 8 GroupNorm apply, code im2col, LayerNorm, ISTFT
+        # (24 with GEMM chains: front end, 8 conv3, first c_attn, 12 chains, last fc2, head; 58 without)
+        n_gemm = launches // args.steps - 23
         gemm_flops = GEMM_FLOPS_PER_TOKEN * total_tokens
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         # a burst region (tens of ms at full clocks) is compared with the burst peak; the sustained block
@@ -481,7 +486,7 @@ def run_ours(args):
         peak = peaks["tflops_burst"]
         traffic, traffic_src = latest_traffic() if args.workload == "c2" else (None, None)
         roofline = {
-            "kernel": "gemm_tc05_2cta_kernel (tcgen05 cta_group::2 GEMM / implicit conv1d; all dense layers)",
+            "kernel": "gemm_tc05_2cta_kernel (tcgen05 cta_group::2 GEMM / implicit conv1d; all dense layers;)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": f"{peaks['source']} bf16_tflops (BURST: the timed region is {burst_s * 1e3:.0f} ms of kernels at "
@@ -636,6 +641,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the config-3 strong-scaling block")
     ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 / config-1 latency block")
+    ap.add_argument("--chain", action="store_true", help="A/B: per-block GEMM chains (one persistent launch for c_proj -> fc1 -> fc2 -> next c_attn)")
     ap.add_argument("--istft-tile", type=int, default=0, help="A/B: output hops per ISTFT CTA (12 or 28)")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: plain stream-ordered launches instead of programmatic dependent launch")
     args = ap.parse_args()

@@ -169,6 +169,12 @@ int b200codec_set_frontend_fold(int mode);
  * times as many. Every output element sees the same K order, so results are bit-identical. A/B switch. */
 int b200codec_set_gemm_narrow_tiles(int on);
 
+/* GEMM chains (default OFF): c_proj -> fc1 -> fc2 -> the next block's c_attn of every transformer block run
+ * as one persistent launch whose tiles wait for the 256-row block they read (csrc/gemm_tc05_2cta.cuh)
+ * instead of four launches that each drain the grid. Same arithmetic per element. Measured: no faster than
+ * the programmatic-dependent-launch chain at config 2 and slower at small M; A/B switch. */
+int b200codec_set_gemm_chain(int on);
+
 /* Output hops per ISTFT CTA: 12 (8 warps, two CTAs per SM) or 28 (16 warps, one CTA per SM, less halo
  * recomputation: a tile of H hops transforms H + 4 frames); 0 (default) picks 28 when that still gives every
  * SM a CTA. Same samples either way. A/B switch. */

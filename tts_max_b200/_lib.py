@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200codec_set_zero_copy_output": (c_int, [c_int]),
     "b200codec_set_gemm_narrow_tiles": (c_int, [c_int]),
     "b200codec_set_istft_tile": (c_int, [c_int]),
+    "b200codec_set_gemm_chain": (c_int, [c_int]),
     "b200codec_set_frontend_fold": (c_int, [c_int]),
     "b200codec_set_pdl": (c_int, [c_int]),
     "b200codec_samples_per_token": (c_int, [c_void_p]),

@@ -31,6 +31,11 @@ int g_use_pdl = 1;
 // 2 = folded, fp32 FMA lookup kernel; 0 = 8 -> 1024 lookup + conv7 GEMM on 16-bit operands
 static int g_frontend_fold = 1;
 static int g_zero_copy_out = 1;  // decode_host: write PCM directly into pinned host memory
+// c_proj -> fc1 -> fc2 -> next c_attn of a transformer block as ONE persistent launch (gemm_tc05_2cta.cuh).
+// OFF by default: measured on config 2 it is within noise of the programmatic-dependent-launch chain of four
+// kernels (3.22-3.30 vs 3.25-3.28 ms per step) and it is slower at small M, where a chain serialises on its
+// single m-block (config 1: 1.41 vs 1.06 ms; config 5: 4.88 vs 4.20 ms). Kept as an A/B switch with its tests.
+static int g_gemm_chain = 0;
 
 static thread_local char g_err[1024] = {0};
 
@@ -159,6 +164,8 @@ struct B200Codec {
     void* u_fin = nullptr;  // out_proj + swish output, operand dtype [rows_last, C]
     double* gn_stats = nullptr;
     size_t gn_stats_bytes = 0;
+    uint32_t* chain_ctr = nullptr;   // GEMM-chain m-block counters, behind the statistics (zeroed with them)
+    size_t stats_zero_bytes = 0;     // bytes of gn_stats + chain_ctr to clear at the start of a decode
     int gn_slots = 8;  // GroupNorm layers: 8 in the backbone + 2 per upsampler stage
     // plan (row space) cache; plan i > 0 is the row space after upsampler stage i - 1
     // (every length, offset and gap of plan 0 multiplied by the product of the strides so far)
@@ -571,9 +578,9 @@ struct NormFuse {
     float ss_in_scale = 1.f;       // consume: its inverse
 };
 
-int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
-         bool out_fp32, int ldc, int n_store, const float* bias, const float* residual, int act,
-         bool mask_rows, cudaStream_t s, const NormFuse& nf = NormFuse()) {
+GemmCall gemm_call(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
+                   bool out_fp32, int ldc, int n_store, const float* bias, const float* residual, int act,
+                   bool mask_rows, const NormFuse& nf = NormFuse()) {
     GemmCall c;
     c.precision = h->cfg.precision;
     c.a = a;
@@ -601,7 +608,13 @@ int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, v
     c.gn_row_utt = h->rs.row_utt;
     c.out16_scale = nf.out16_scale;
     c.ss_in_scale = nf.ss_in_scale;
-    return launch_gemm(c, s);
+    return c;
+}
+
+int gemm(B200Codec* h, const void* a, int Cin, const void* w, int N, int taps, void* out,
+         bool out_fp32, int ldc, int n_store, const float* bias, const float* residual, int act,
+         bool mask_rows, cudaStream_t s, const NormFuse& nf = NormFuse()) {
+    return launch_gemm(gemm_call(h, a, Cin, w, N, taps, out, out_fp32, ldc, n_store, bias, residual, act, mask_rows, nf), s);
 }
 
 // ResnetBlock (decoder_modules.py:201-223) on one row space at C channels:
@@ -825,7 +838,7 @@ int forward(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cuda
 int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev, cudaStream_t s) {
     const int C = h->C, prec = h->cfg.precision;
     const RowSpace& rs = h->rs;
-    B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, sizeof(double) * h->gn_slots * rs.n_utts * 64, s));
+    B200_CUDA_OK(cudaMemsetAsync(h->gn_stats, 0, h->stats_zero_bytes, s));
     // GroupNorm statistics slot k (k = 2 * block + {0: norm1, 1: norm2}) of utterance u, group g:
     // gn_stats[((k * n_utts + u) * 32 + g) * 2 + {sum, sumsq}]
     const bool gn_fused = gn_stats_in_gemm(rs.rows, C);
@@ -887,6 +900,16 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
     if (resnet_block(h, h->res[0], 0, s, NormFuse(), gn0_done, gn_slot(2))) return 1;
     if (resnet_block(h, h->res[1], 2, s, produce, gn_fused, nullptr)) return 1;
     if (tap_stage(h, "prior_net", h->x, 4, C, C, rs.rows, 0, s)) return 1;
+    // Transformer blocks (decoder_modules.py:311-314). With the fused RMSNorm every linear of a block reads,
+    // per 256-row block, only what the previous linear wrote in that block, so c_proj -> fc1 -> fc2 -> the
+    // next block's c_attn run as ONE persistent launch (a GEMM chain); the last block's fc2 also reduces
+    // GroupNorm statistics and stays a launch of its own.
+    const bool chain = fuse_rms && g_gemm_chain != 0;
+    const size_t num_m = (static_cast<size_t>(rs.rows) + 255) / 256;
+    auto qkv_call = [&](int l) {
+        return gemm_call(h, fuse_rms ? h->xb : h->an, C, h->layers[l].qkv, 3 * C, 1, h->qkv, false, 3 * C, 3 * C, nullptr,
+                         nullptr, kActNone, false, consume);
+    };
     for (int l = 0; l < h->L; ++l) {
         const LayerW& w = h->layers[l];
         const bool last = l + 1 == h->L;
@@ -894,37 +917,55 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
             Stage t(h, "rmsnorm", s);
             RUN(launch_rmsnorm(prec, h->x, nullptr, rs.rows, C, 1e-6f, h->an, s));
         }
-        {
+        if (!chain || l == 0) {
             Stage t(h, "qkv_gemm", s);
-            RUN(gemm(h, fuse_rms ? h->xb : h->an, C, w.qkv, 3 * C, 1, h->qkv, false, 3 * C, 3 * C,
-                     nullptr, nullptr, kActNone, false, s, consume));
+            RUN(launch_gemm(qkv_call(l), s));
         }
         {
             Stage t(h, "attention", s);
             RUN(run_attention(prec, h->qkv, rs, h->H, h->y, s));
         }
-        {
-            Stage t(h, "proj_gemm", s);
-            RUN(gemm(h, h->y, C, w.proj, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s,
-                     produce));
+        const GemmCall proj = gemm_call(h, h->y, C, w.proj, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, produce);
+        const GemmCall fc1 = gemm_call(h, fuse_rms ? h->xb : h->an, C, w.fc1, 4 * C, 1, h->f, false, 4 * C, 4 * C, nullptr,
+                                       nullptr, kActSilu, false, consume);
+        NormFuse f2 = produce;
+        if (last) {
+            f2 = NormFuse();
+            f2.gn_stats = gn_slot(4);  // post_net.0's first GroupNorm reads this x
         }
-        if (!fuse_rms) {
-            Stage t(h, "rmsnorm", s);
-            RUN(launch_rmsnorm(prec, h->x, nullptr, rs.rows, C, 1e-6f, h->an, s));
-        }
-        {
-            Stage t(h, "fc1_gemm", s);
-            RUN(gemm(h, fuse_rms ? h->xb : h->an, C, w.fc1, 4 * C, 1, h->f, false, 4 * C, 4 * C,
-                     nullptr, nullptr, kActSilu, false, s, consume));
-        }
-        {
-            Stage t(h, "fc2_gemm", s);
-            NormFuse f2 = produce;
-            if (last) {
-                f2 = NormFuse();
-                f2.gn_stats = gn_slot(4);  // post_net.0's first GroupNorm reads this x
+        const GemmCall fc2 = gemm_call(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, f2);
+        if (chain) {
+            GemmCall calls[4] = {proj, fc1, fc2, fc2};
+            int n = 2;
+            if (!last) {
+                calls[3] = qkv_call(l + 1);
+                n = 4;
             }
-            RUN(gemm(h, h->f, 4 * C, w.fc2, C, 1, h->x, true, C, C, nullptr, h->x, kActNone, false, s, f2));
+            {
+                Stage t(h, "chain_gemm", s);
+                RUN(launch_gemm_chain(calls, n, h->chain_ctr + static_cast<size_t>(l) * 4 * num_m, s));
+            }
+            if (last) {
+                Stage t(h, "fc2_gemm", s);
+                RUN(launch_gemm(fc2, s));
+            }
+        } else {
+            {
+                Stage t(h, "proj_gemm", s);
+                RUN(launch_gemm(proj, s));
+            }
+            if (!fuse_rms) {
+                Stage t(h, "rmsnorm", s);
+                RUN(launch_rmsnorm(prec, h->x, nullptr, rs.rows, C, 1e-6f, h->an, s));
+            }
+            {
+                Stage t(h, "fc1_gemm", s);
+                RUN(launch_gemm(fc1, s));
+            }
+            {
+                Stage t(h, "fc2_gemm", s);
+                RUN(launch_gemm(fc2, s));
+            }
         }
         if (l == 0 && tap_stage(h, "tblock0", h->x, 4, C, C, rs.rows, 0, s)) return 1;
     }
@@ -1446,8 +1487,12 @@ static int decode_varlen_locked(B200Codec* h, const void* ids_dev, int id_type,
     B200_CHECK(ids_dev && wav_dev, "decode: null device buffer");
     // 8 GroupNorm layers x [n_utts][32 groups][sum, sumsq] fp64
     // + one float2 [n_utts][32] (mean, rstd) scratch per GroupNorm layer
-    const size_t need = sizeof(double) * h->gn_slots * static_cast<size_t>(n_utts) * 64 +
-                        sizeof(float2) * h->gn_slots * static_cast<size_t>(n_utts) * 32;
+    // + per transformer block, 4 GEMMs x ceil(rows / 256) m-block counters of the GEMM chains
+    const size_t gn_bytes = (sizeof(double) * h->gn_slots * static_cast<size_t>(n_utts) * 64 + 255) & ~static_cast<size_t>(255);
+    const size_t num_m = (static_cast<size_t>(h->rs.rows) + 255) / 256;
+    const size_t ctr_bytes = sizeof(uint32_t) * static_cast<size_t>(h->L) * 4 * num_m;
+    const size_t need = gn_bytes + ctr_bytes;
+    h->stats_zero_bytes = need;
     if (h->gn_stats_bytes < need) {
         h->generation++;
         if (h->gn_stats) B200_CUDA_OK(cudaFree(h->gn_stats));
@@ -1456,6 +1501,7 @@ static int decode_varlen_locked(B200Codec* h, const void* ids_dev, int id_type,
         B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->gn_stats), need * 2));
         h->gn_stats_bytes = need * 2;
     }
+    h->chain_ctr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(h->gn_stats) + gn_bytes);
     const int rc = forward(h, ids_dev, id_type, wav_dev, s);
     if (h->profiling) {
         cudaStreamSynchronize(s);
@@ -1603,6 +1649,11 @@ int b200codec_set_frontend_fold(int mode) {
     B200_CHECK(mode >= 0 && mode <= 2, "front-end mode must be 0 (lookup + conv7 GEMM), 1 (folded, tensor cores) "
                                        "or 2 (folded, fp32 FMA kernel)");
     g_frontend_fold = mode;
+    return 0;
+}
+
+int b200codec_set_gemm_chain(int on) {
+    g_gemm_chain = on != 0;
     return 0;
 }
 

@@ -4,7 +4,15 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+#include <cstring>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <queue>
 #include <unordered_map>
+#include <vector>
 
 #include "kernels.h"
 
@@ -229,7 +237,10 @@ unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
 
 int g_gemm_narrow_tiles = 1;  // A/B: 0 = 256-wide tiles only
 
-int launch_gemm(const GemmCall& c, cudaStream_t stream) {
+namespace {
+
+// validation and GemmParams of one call (shared by plain launches and chains)
+int fill_params(const GemmCall& c, GemmParams* out) {
     B200_CHECK(c.precision == kPrecBf16 || c.precision == kPrecFp16,
                "gemm: unsupported precision %d", c.precision);
     const int block_k = 64;
@@ -238,12 +249,6 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
                c.n_store, c.ldc);
     B200_CHECK(c.taps >= 1 && (c.tap_pad >= 0 || c.taps % 2 == 1), "gemm: even tap counts need an explicit tap_pad");
     B200_CHECK(c.residual == nullptr || c.out_fp32, "gemm: a residual requires fp32 output");
-    if (c.a_rows <= 0) return 0;
-    const bool wide = gemm_is_wide(c);
-    alignas(64) CUtensorMap ta, tb;
-    if (c.tmap_a != nullptr) ta = *static_cast<const CUtensorMap*>(c.tmap_a);
-    if (c.tmap_b != nullptr) tb = *static_cast<const CUtensorMap*>(c.tmap_b);
-    if (encode_gemm_tmaps(c, c.tmap_a ? nullptr : &ta, c.tmap_b ? nullptr : &tb)) return 1;
     GemmParams p;
     p.M = c.a_rows;
     p.n_store = c.n_store;
@@ -270,7 +275,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
 #endif
     const bool fused = c.ss_in != nullptr || c.out16 != nullptr || c.ss_out != nullptr;
     B200_CHECK(!fused || gemm_kind(c) == kGemm2Cta,
-               "gemm: the RMSNorm-fused epilogue needs the CTA-pair kernel (N % 256 == 0)");
+               "gemm: the RMSNorm-fused epilogue needs the CTA-pair kernel (N %% 256 == 0)");
     B200_CHECK(c.out16 == nullptr || c.out_fp32, "gemm: out16 requires fp32 output");
     B200_CHECK(c.ss_out == nullptr || (c.out_fp32 && c.n_store == 1024),
                "gemm: ss_out requires fp32 output with N == 1024");
@@ -284,54 +289,204 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
                "gemm: GroupNorm statistics need the CTA-pair kernel, fp32 output, N == 1024 and a row -> utterance map");
     p.has32 = c.out_fp32 ? 1 : 0;
     p.has16 = (!c.out_fp32 || c.out16 != nullptr) ? 1 : 0;
-    if (gemm_kind(c) == kGemm2Cta) {
-        // the epilogue stores with TMA: fp32 boxes of 32 x 32 (128-byte rows), 16-bit output
-        // (or operand copy) boxes of 32 x 32 (64-byte rows)
-        const int dt16 = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
-        alignas(64) CUtensorMap to32, to16;
-        to32 = ta;  // placeholders for the map this launch does not use
-        to16 = ta;
-        if (c.out_fp32) {
-            if (make_tmap_box(&to32, c.out, kTmapF32, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
-            if (c.out16 != nullptr &&
-                make_tmap_box(&to16, c.out16, dt16, c.a_rows, c.n_store, c.ld16, kGemm2ChunkCols, 32))
-                return 1;
-        } else {
-            if (make_tmap_box(&to16, c.out, dt16, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
-        }
-        // Small M: 256 x 64 tiles when the 256-wide tiling would leave most CTA pairs without a tile
-        // (B = 1 serving, config 1). A narrow tile costs ~0.6 of a wide one (its K loop is bounded by
-        // the A-tile load), so it pays when four times the tiles still fit in fewer weighted rounds.
-        const int pairs = kNumSMs / 2;
-        const int tiles256 = ((c.a_rows + 255) / 256) * (c.n_store / 256);
-        const int rounds256 = (tiles256 + pairs - 1) / pairs;
-        const int rounds64 = (4 * tiles256 + pairs - 1) / pairs;
-        const bool narrow = g_gemm_narrow_tiles && c.tmap_b == nullptr && rounds64 * 60 < rounds256 * 95;
-        if (narrow) {
-            const int dtb = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
-            if (make_tmap_2d(&tb, c.w, dtb, c.N, static_cast<uint64_t>(c.taps) * c.Cin,
-                             static_cast<uint64_t>(c.taps) * c.Cin, 32))
-                return 1;
-            if (p.gn_stats != nullptr) {
-                if (c.precision == kPrecBf16)
-                    return launch_gemm_tc05_2cta<__nv_bfloat16, true, 64>(ta, tb, to32, to16, p, stream);
-                return launch_gemm_tc05_2cta<__half, true, 64>(ta, tb, to32, to16, p, stream);
-            }
-            if (c.precision == kPrecBf16)
-                return launch_gemm_tc05_2cta<__nv_bfloat16, false, 64>(ta, tb, to32, to16, p, stream);
-            return launch_gemm_tc05_2cta<__half, false, 64>(ta, tb, to32, to16, p, stream);
-        }
-        if (p.gn_stats != nullptr) {
-            if (c.precision == kPrecBf16)
-                return launch_gemm_tc05_2cta<__nv_bfloat16, true>(ta, tb, to32, to16, p, stream);
-            return launch_gemm_tc05_2cta<__half, true>(ta, tb, to32, to16, p, stream);
-        }
-        if (c.precision == kPrecBf16)
-            return launch_gemm_tc05_2cta<__nv_bfloat16, false>(ta, tb, to32, to16, p, stream);
-        return launch_gemm_tc05_2cta<__half, false>(ta, tb, to32, to16, p, stream);
+    *out = p;
+    return 0;
+}
+
+// Small M: 256 x 64 tiles when the 256-wide tiling would leave most CTA pairs without a tile
+// (B = 1 serving, config 1). A narrow tile costs ~0.6 of a wide one (its K loop is bounded by
+// the A-tile load), so it pays when four times the tiles still fit in fewer weighted rounds.
+bool want_narrow(int a_rows, int n_store) {
+    const int pairs = kNumSMs / 2;
+    const int tiles256 = ((a_rows + 255) / 256) * (n_store / 256);
+    const int rounds256 = (tiles256 + pairs - 1) / pairs;
+    const int rounds64 = (4 * tiles256 + pairs - 1) / pairs;
+    return g_gemm_narrow_tiles && rounds64 * 60 < rounds256 * 95;
+}
+
+// tensor maps of one CTA-pair GEMM: A, B (box of block_n / 2 weight rows), fp32 / 16-bit output boxes
+int fill_maps_2cta(const GemmCall& c, int block_n, CUtensorMap* ta, CUtensorMap* tb, CUtensorMap* to32,
+                   CUtensorMap* to16) {
+    const int dt16 = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
+    if (c.tmap_a != nullptr) *ta = *static_cast<const CUtensorMap*>(c.tmap_a);
+    else if (make_tmap_2d(ta, c.a, dt16, c.a_rows, c.Cin, c.Cin, kGemmBlockM)) return 1;
+    if (c.tmap_b != nullptr && block_n == 256) *tb = *static_cast<const CUtensorMap*>(c.tmap_b);
+    else if (make_tmap_2d(tb, c.w, dt16, c.N, static_cast<uint64_t>(c.taps) * c.Cin,
+                          static_cast<uint64_t>(c.taps) * c.Cin, block_n / 2))
+        return 1;
+    // the epilogue stores with TMA: fp32 boxes of 32 x 32 (128-byte rows), 16-bit output
+    // (or operand copy) boxes of 32 x 32 (64-byte rows)
+    *to32 = *ta;  // placeholders for the map this GEMM does not use
+    *to16 = *ta;
+    if (c.out_fp32) {
+        if (make_tmap_box(to32, c.out, kTmapF32, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
+        if (c.out16 != nullptr &&
+            make_tmap_box(to16, c.out16, dt16, c.a_rows, c.n_store, c.ld16, kGemm2ChunkCols, 32))
+            return 1;
+    } else {
+        if (make_tmap_box(to16, c.out, dt16, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
     }
+    return 0;
+}
+
+template <bool kChain>
+int launch_2cta(int precision, bool gn, bool narrow, const ChainMaps& maps, const ChainParams& cp, cudaStream_t s) {
+    const bool bf = precision == kPrecBf16;
+    if (narrow) {
+        if (gn) return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, true, 64, kChain>(maps, cp, s)
+                          : launch_gemm_tc05_2cta<__half, true, 64, kChain>(maps, cp, s);
+        return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, false, 64, kChain>(maps, cp, s)
+                  : launch_gemm_tc05_2cta<__half, false, 64, kChain>(maps, cp, s);
+    }
+    if (gn) return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, true, 256, kChain>(maps, cp, s)
+                      : launch_gemm_tc05_2cta<__half, true, 256, kChain>(maps, cp, s);
+    return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, false, 256, kChain>(maps, cp, s)
+              : launch_gemm_tc05_2cta<__half, false, 256, kChain>(maps, cp, s);
+}
+
+}  // namespace
+
+int launch_gemm(const GemmCall& c, cudaStream_t stream) {
+    GemmParams p;
+    if (fill_params(c, &p)) return 1;
+    if (c.a_rows <= 0) return 0;
+    if (gemm_kind(c) == kGemm2Cta) {
+        const bool narrow = c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store);
+        const int block_n = narrow ? 64 : 256;
+        alignas(64) ChainMaps maps;
+        ChainParams cp{};
+        if (fill_maps_2cta(c, block_n, &maps.a[0], &maps.b[0], &maps.o32[0], &maps.o16[0])) return 1;
+        cp.n_gemm = 1;
+        cp.num_m = (c.a_rows + 255) / 256;
+        cp.num_n[0] = c.n_store / block_n;
+        cp.tile_end[0] = cp.num_m * cp.num_n[0];
+        cp.full[0] = 0;
+        cp.counters = nullptr;
+        cp.g[0] = p;
+        return launch_2cta<false>(c.precision, p.gn_stats != nullptr, narrow, maps, cp, stream);
+    }
+    const bool wide = gemm_is_wide(c);
+    alignas(64) CUtensorMap ta, tb;
+    if (c.tmap_a != nullptr) ta = *static_cast<const CUtensorMap*>(c.tmap_a);
+    if (c.tmap_b != nullptr) tb = *static_cast<const CUtensorMap*>(c.tmap_b);
+    if (encode_gemm_tmaps(c, c.tmap_a ? nullptr : &ta, c.tmap_b ? nullptr : &tb)) return 1;
     if (c.precision == kPrecBf16) return dispatch<__nv_bfloat16>(c, ta, tb, p, wide, stream);
     return dispatch<__half>(c, ta, tb, p, wide, stream);
+}
+
+namespace {
+
+// Per-cluster tile lists of a chain (see ChainParams::sched): tiles are handed out in the global order,
+// each to the cluster that becomes free first under the cost model "K blocks + a fixed turnaround". Every
+// list is increasing, which is what the chain's no-deadlock argument needs. Lists depend on the shapes
+// only, so they are built once per shape and cached on the device (never freed: a few KB each).
+struct SchedKey {
+    int dev, n, clusters, num_m, num_n[kChainMax], kb[kChainMax];
+    bool operator<(const SchedKey& o) const { return std::memcmp(this, &o, sizeof(SchedKey)) < 0; }
+};
+struct SchedBuf {
+    int32_t* dev = nullptr;
+    int stride = 0;
+};
+
+int chain_schedule(const ChainParams& cp, const int* kb, int clusters, SchedBuf* out) {
+    static std::map<SchedKey, SchedBuf> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    SchedKey key;
+    std::memset(&key, 0, sizeof(key));
+    cudaGetDevice(&key.dev);
+    key.n = cp.n_gemm;
+    key.clusters = clusters;
+    key.num_m = cp.num_m;
+    for (int i = 0; i < cp.n_gemm; ++i) {
+        key.num_n[i] = cp.num_n[i];
+        key.kb[i] = kb[i];
+    }
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return 0;
+    }
+    const int total = cp.tile_end[cp.n_gemm - 1];
+    std::vector<std::vector<int32_t>> lists(clusters);
+    // (time the cluster becomes free, cluster): smallest first, ties to the lower cluster id
+    using Slot = std::pair<long long, int>;
+    std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> free_at;
+    for (int c = 0; c < clusters; ++c) free_at.push({0, c});
+    int g = 0;
+    for (int t = 0; t < total; ++t) {
+        while (t >= cp.tile_end[g]) ++g;
+        Slot sl = free_at.top();
+        free_at.pop();
+        lists[sl.second].push_back(t);
+        free_at.push({sl.first + kb[g] + 2, sl.second});
+    }
+    size_t longest = 0;
+    for (auto& l : lists) longest = std::max(longest, l.size());
+    SchedBuf buf;
+    buf.stride = static_cast<int>(longest) + 1;
+    std::vector<int32_t> host(static_cast<size_t>(clusters) * buf.stride, -1);
+    for (int c = 0; c < clusters; ++c) std::copy(lists[c].begin(), lists[c].end(), host.begin() + static_cast<size_t>(c) * buf.stride);
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&buf.dev), host.size() * sizeof(int32_t)));
+    B200_CUDA_OK(cudaMemcpy(buf.dev, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (cache.size() >= 4096) cache.clear();  // the buffers stay allocated (a few KB each); only the memo is bounded
+    cache[key] = buf;
+    *out = buf;
+    return 0;
+}
+
+}  // namespace
+
+bool gemm_chain_supported(const GemmCall* calls, int n) {
+    if (n < 2 || n > kChainMax) return false;
+    for (int i = 0; i < n; ++i) {
+        const GemmCall& c = calls[i];
+        if (gemm_kind(c) != kGemm2Cta || c.taps != 1 || c.gn_stats != nullptr || c.a_rows != calls[0].a_rows ||
+            c.precision != calls[0].precision || c.row_valid != nullptr)
+            return false;
+    }
+    return true;
+}
+
+int launch_gemm_chain(const GemmCall* calls, int n, uint32_t* counters, cudaStream_t stream) {
+    B200_CHECK(gemm_chain_supported(calls, n), "gemm chain: 2 to %d plain linears (no taps, no GroupNorm statistics) "
+               "on the CTA-pair kernel with a common row count", kChainMax);
+    B200_CHECK(counters != nullptr, "gemm chain: null counters");
+    if (calls[0].a_rows <= 0) return 0;
+    const bool narrow = want_narrow(calls[0].a_rows, 1024);
+    const int block_n = narrow ? 64 : 256;
+    alignas(64) ChainMaps maps;
+    ChainParams cp{};
+    cp.n_gemm = n;
+    cp.num_m = (calls[0].a_rows + 255) / 256;
+    cp.counters = counters;
+    int end = 0;
+    for (int i = 0; i < n; ++i) {
+        if (fill_params(calls[i], &cp.g[i])) return 1;
+        if (fill_maps_2cta(calls[i], block_n, &maps.a[i], &maps.b[i], &maps.o32[i], &maps.o16[i])) return 1;
+        cp.num_n[i] = calls[i].n_store / block_n;
+        end += cp.num_m * cp.num_n[i];
+        cp.tile_end[i] = end;
+        cp.full[i] = 16u * static_cast<uint32_t>(cp.num_n[i]);  // 8 epilogue warps x 2 CTAs per tile
+    }
+    int kb[kChainMax] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) kb[i] = cp.g[i].taps * cp.g[i].k_blocks_per_tap;
+    int clusters = end < kNumSMs / 2 ? end : kNumSMs / 2;
+    SchedBuf sched;
+    if (chain_schedule(cp, kb, clusters, &sched)) return 1;
+    cp.sched = sched.dev;
+    cp.sched_stride = sched.stride;
+    {
+        static const char* e = getenv("B200_CHAIN_DBG");  // timing experiments (tools), never set in production
+        cp.dbg = e ? atoi(e) : 0;
+    }
+    for (int i = n; i < kChainMax; ++i) {  // unused slots: valid descriptors, never indexed
+        maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; maps.o32[i] = maps.o32[0]; maps.o16[i] = maps.o16[0];
+        cp.tile_end[i] = end;
+        cp.num_n[i] = 1;
+    }
+    return launch_2cta<true>(calls[0].precision, false, narrow, maps, cp, stream);
 }
 
 int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,

@@ -139,12 +139,70 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
 // to work (the K loop of a narrow tile is bounded by the A-tile load, ~0.15 us per K-block instead of
 // 0.26). Every output element sees the same K order, so the tile width never changes results. The
 // shared-memory stage keeps its 256-wide size; TMEM holds 2 x BLOCK_N columns.
-template <typename InT, bool kGnStats, int BLOCK_N>
+// ---------------------------------------------------------------------------------------------------
+// GEMM chains (kChain). Inside a transformer block c_proj -> fc1 -> fc2 -> (next block's) c_attn are
+// row-block local: RMSNorm is per row and already travels as sum-of-squares partials, so a 256-row block
+// of GEMM g+1 needs nothing but the same 256 rows of GEMM g. As separate launches every boundary drains
+// the grid (griddepcontrol.wait), pays ~5 us of prologue / exposed epilogue / teardown and rounds each
+// GEMM up to whole waves of 74 tiles (86 % for the N = 1024 GEMMs). Here ONE persistent launch walks the
+// tiles of up to four GEMMs in a single global order (GEMM by GEMM, m-block major, n fastest; cluster c
+// takes tiles c, c + 74, ...). A tile of GEMM g > 0 waits until every tile of GEMM g-1 in its m-block has
+// been stored: the epilogue warps count themselves into counters[g][m_blk] with a gpu-scope release after
+// their TMA stores completed, the TMA producer (and the epilogue warps, for the residual / row-scale
+// reads) acquire it before touching that m-block. Tiles only ever wait for tiles EARLIER in the order and
+// all clusters are co-resident (grid <= 74 clusters of one CTA per SM), so the smallest unfinished tile can
+// always run: no deadlock. Weights are constants: their loads never wait.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kChainMax = 4;
+
+struct ChainMaps {
+    CUtensorMap a[kChainMax], b[kChainMax], o32[kChainMax], o16[kChainMax];
+};
+struct ChainParams {
+    int n_gemm;                  // 1 = plain GEMM
+    int num_m;                   // m-blocks of 256 rows (all GEMMs of a chain share M)
+    int tile_end[kChainMax];     // cumulative tile counts in the global order
+    int num_n[kChainMax];        // n-tiles per m-block
+    uint32_t full[kChainMax];    // counter value of a finished m-block: 16 epilogue warps x num_n
+    uint32_t* counters;          // [n_gemm][num_m], zero on entry (chains only)
+    // chains: the tiles each cluster walks, in increasing global order, -1 terminated:
+    // sched[cluster * sched_stride + k]. Built on the host by in-order list scheduling on the tiles' K
+    // lengths, because a plain round robin gives some clusters two of fc2's long (K = 4096) tiles and
+    // others one -- 4 of ~21 tile units of imbalance (measured: the chain was then no faster in the step).
+    const int32_t* sched;
+    int sched_stride;
+    int dbg;  // timing experiments only (tools): 1 no store-completion wait, 2 no epilogue acquire, 4 no producer fence, 8 no publish
+    GemmParams g[kChainMax];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders async-proxy (TMA) accesses to global memory against generic-proxy accesses of this thread
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Bounded wait for an m-block of the previous GEMM of the chain (a protocol bug must trap, not hang).
+__device__ __forceinline__ void chain_wait(const uint32_t* ctr, uint32_t full) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(ctr) < full) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) {
+            printf("b200codec: GEMM chain dependency timed out (block %d thread %d: %u of %u)\n", blockIdx.x,
+                   threadIdx.x, ld_acquire_gpu(ctr), full);
+            __trap();
+        }
+    }
+}
+
+template <typename InT, bool kGnStats, int BLOCK_N, bool kChain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
-gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                      const __grid_constant__ CUtensorMap tmap_b,
-                      const __grid_constant__ CUtensorMap tmap_o32,
-                      const __grid_constant__ CUtensorMap tmap_o16, const GemmParams p) {
+gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams cp) {
+    const GemmParams& p = cp.g[0];  // plain GEMM: the only one; chains: per-tile parameters are cp.g[g]
     using SM = Gemm2Smem;
     static_assert(BLOCK_N == 256 || BLOCK_N == 64, "tile width");
     constexpr int kHalfN = BLOCK_N / 2;  // B rows staged by each CTA = accumulator columns per epilogue warp
@@ -171,20 +229,42 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
-    const int num_m = (p.M + 255) / 256;
-    const int num_n = p.n_store / BLOCK_N;
-    const int num_tiles = num_m * num_n;
-    const int num_kb = p.taps * p.k_blocks_per_tap;
+    const int num_tiles = cp.tile_end[kChain ? cp.n_gemm - 1 : 0];
     const int cluster_id = blockIdx.x >> 1;
+    // the tiles of this cluster: a host-built list (chains) or every num_clusters-th tile. next_tile is
+    // called at the TOP of a tile's body, so the list entry (an L2 hit, ~0.6 us) is in flight during the tile
     const int num_clusters = gridDim.x >> 1;
+    auto first_tile = [&]() -> int {
+        if constexpr (kChain) return __ldg(cp.sched + static_cast<size_t>(cluster_id) * cp.sched_stride);
+        return cluster_id < num_tiles ? cluster_id : -1;
+    };
+    auto next_tile = [&](int it, int tile) -> int {
+        if constexpr (kChain) return __ldg(cp.sched + static_cast<size_t>(cluster_id) * cp.sched_stride + it);
+        const int t = tile + num_clusters;
+        return t < num_tiles ? t : -1;
+    };
+    // global tile index -> (GEMM of the chain, m-block, n-block); n fastest: the clusters that share one
+    // A (activation) tile run concurrently, so it is fetched from HBM once; the weight tiles are few and
+    // stay in L2
+    auto decode_tile = [&](int tile, int& g, int& m_blk, int& n_blk) {
+        g = 0;
+        int local = tile;
+        if constexpr (kChain) {
+            while (g + 1 < cp.n_gemm && tile >= cp.tile_end[g]) ++g;
+            if (g > 0) local = tile - cp.tile_end[g - 1];
+        }
+        const int nn = cp.num_n[g];
+        m_blk = local / nn;
+        n_blk = local - m_blk * nn;
+    };
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b[0]);
     }
     if (warp == 3 && lane == 0) {
-        if (p.has32) tma_prefetch_desc(&tmap_o32);
-        if (p.has16) tma_prefetch_desc(&tmap_o16);
+        if (p.has32) tma_prefetch_desc(&maps.o32[0]);
+        if (p.has16) tma_prefetch_desc(&maps.o16[0]);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -216,23 +296,34 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                // n fastest: the clusters that share one A (activation) tile run concurrently, so
-                // it is fetched from HBM once; the weight tiles are few and stay in L2
-                const int n_blk = tile % num_n;
-                const int m_blk = tile / num_n;
+            for (int it = 0, tile = first_tile(), tile_next; tile >= 0; tile = tile_next) {
+                tile_next = next_tile(++it, tile);
+                int g, m_blk, n_blk;
+                decode_tile(tile, g, m_blk, n_blk);
+                const GemmParams& pg = cp.g[g];
+                const CUtensorMap* tmap_a = &maps.a[g];
+                const CUtensorMap* tmap_b = &maps.b[g];
+                const int num_kb = pg.taps * pg.k_blocks_per_tap;
                 const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
                 const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * kHalfN;
+                bool dep_pending = kChain && g > 0;  // this m-block of the previous GEMM must be stored first
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     // both CTAs' bytes complete on the leader's barrier
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
                     const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                    const int tap = kb / p.k_blocks_per_tap;
-                    const int kc = kb - tap * p.k_blocks_per_tap;
+                    const int tap = kb / pg.k_blocks_per_tap;
+                    const int kc = kb - tap * pg.k_blocks_per_tap;
                     const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
-                    tma_load_2d_2cta(sa, &tmap_a, full_leader, kc * BLOCK_K, m0 + tap - p.tap_pad);
-                    tma_load_2d_2cta(sa + SM::kABytes, &tmap_b, full_leader, kb * BLOCK_K, n0);
+                    tma_load_2d_2cta(sa + SM::kABytes, tmap_b, full_leader, kb * BLOCK_K, n0);  // weights never wait
+                    if constexpr (kChain) {
+                        if (dep_pending) {
+                            if (!(cp.dbg & 8)) chain_wait(cp.counters + (g - 1) * cp.num_m + m_blk, cp.full[g - 1]);
+                            if (!(cp.dbg & 4)) fence_proxy_async_all();  // the acquired rows are read through the async proxy (TMA)
+                            dep_pending = false;
+                        }
+                    }
+                    tma_load_2d_2cta(sa, tmap_a, full_leader, kc * BLOCK_K, m0 + tap - pg.tap_pad);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -251,7 +342,11 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t acc_phase = 0;
             int trace_tile = 0;
             (void)trace_tile;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int it = 0, tile = first_tile(), tile_next; tile >= 0; tile = tile_next) {
+                tile_next = next_tile(++it, tile);
+                int g, m_blk_unused, n_blk_unused;
+                decode_tile(tile, g, m_blk_unused, n_blk_unused);
+                const int num_kb = cp.g[g].taps * cp.g[g].k_blocks_per_tap;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -298,9 +393,6 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t ring16 = box32 + SM::kBox32Bytes;
         const uint32_t row32 = box32 + lane * 128, swz32 = lane & 7;
         const uint32_t row16 = lane * 64, swz16 = (lane >> 1) & 3;
-        const bool has32 = p.has32 != 0;
-        const bool has16 = p.has16 != 0;
-        const bool has_res = has32 && p.residual != nullptr;
         int slot16 = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -308,9 +400,24 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t tmem_empty_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
         int trace_tile = 0;
         (void)trace_tile;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int n_blk = tile % num_n;
-            const int m_blk = tile / num_n;
+        for (int it = 0, tile = first_tile(), tile_next; tile >= 0; tile = tile_next) {
+            tile_next = next_tile(++it, tile);
+            int g, m_blk, n_blk;
+            decode_tile(tile, g, m_blk, n_blk);
+            const GemmParams& p = cp.g[g];  // shadows the kernel-level alias: this tile's GEMM
+            const CUtensorMap* tmap_o32 = &maps.o32[g];
+            const CUtensorMap* tmap_o16 = &maps.o16[g];
+            const bool has32 = p.has32 != 0;
+            const bool has16 = p.has16 != 0;
+            const bool has_res = has32 && p.residual != nullptr;
+            if constexpr (kChain) {
+                // the residual and the row scale of this m-block come from earlier GEMMs of the chain: acquire
+                // before the prefetches below (the counter is long complete by now; the producer waited for it)
+                if (g > 0 && !(cp.dbg & (2 | 8))) {
+                    if (lane == 0) chain_wait(cp.counters + (g - 1) * cp.num_m + m_blk, cp.full[g - 1]);
+                    __syncwarp();
+                }
+            }
             const int row_base = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
             const int row = row_base + lane;
             const bool row_ok = row < p.M;
@@ -486,14 +593,27 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (tr) B200_TRACE(tslot + 3);  // staged + fenced
 #endif
                 if (lane == 0) {
-                    if (has32) tma_store_2d(&tmap_o32, box32, n0, row_base);
-                    if (has16) tma_store_2d(&tmap_o16, buf16, n0, row_base);
+                    if (has32) tma_store_2d(tmap_o32, box32, n0, row_base);
+                    if (has16) tma_store_2d(tmap_o16, buf16, n0, row_base);
                     bulk_commit_group();
 #ifdef B200_GEMM_TRACE
                     if (tr) B200_TRACE(tslot + 4);  // stores issued
 #endif
                 }
                 slot16 ^= 1;
+            }
+            if constexpr (kChain) {
+                // publish this warp's share of the tile to the next GEMM of the chain: its TMA stores have
+                // completed (not merely been read out of the staging boxes), its lanes' row partial sums
+                // are ordered before lane 0 by the warp barrier, then a gpu-scope release
+                if (g + 1 < cp.n_gemm && !(cp.dbg & 8)) {
+                    if (lane == 0 && !(cp.dbg & 1)) {
+                        bulk_wait_group<0>();
+                        fence_proxy_async_all();
+                    }
+                    __syncwarp();
+                    if (lane == 0) red_release_gpu_add(cp.counters + g * cp.num_m + m_blk, 1u);
+                }
             }
             if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(11 + 2 * trace_tile);  // tile drained
             ++trace_tile;
@@ -516,22 +636,18 @@ gemm_tc05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == 2) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
-template <typename InT, bool kGnStats, int BLOCK_N = kGemm2BlockN>
-int launch_gemm_tc05_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to32,
-                          const CUtensorMap& to16, const GemmParams& p, cudaStream_t stream) {
-    auto kern = gemm_tc05_2cta_kernel<InT, kGnStats, BLOCK_N>;
+template <typename InT, bool kGnStats, int BLOCK_N, bool kChain>
+int launch_gemm_tc05_2cta(const ChainMaps& maps, const ChainParams& cp, cudaStream_t stream) {
+    auto kern = gemm_tc05_2cta_kernel<InT, kGnStats, BLOCK_N, kChain>;
     static PerDeviceOnce once;
     if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Gemm2Smem::kTotal));
     }
-    const int num_m = (p.M + 255) / 256;
-    const int num_n = p.n_store / BLOCK_N;
-    int clusters = num_m * num_n;
+    int clusters = cp.tile_end[cp.n_gemm - 1];
     if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
     if (clusters < 1) return 0;
-    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2Smem::kTotal, stream, ta, tb,
-                               to32, to16, p));
+    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2Smem::kTotal, stream, maps, cp));
     return 0;
 }
 

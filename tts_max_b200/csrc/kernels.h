@@ -131,6 +131,11 @@ struct GemmCall {
 };
 constexpr size_t kTmapBytes = 128;
 int launch_gemm(const GemmCall& c, cudaStream_t stream);
+// GEMM chain: calls[0..n) are plain linears over the same rows where calls[i + 1] reads (as its A operand,
+// row scale or residual) only what calls[0..i] wrote in the SAME 256-row block. One persistent launch;
+// `counters` = n * ceil(rows / 256) uint32, zero on entry (see gemm_tc05_2cta.cuh).
+bool gemm_chain_supported(const GemmCall* calls, int n);
+int launch_gemm_chain(const GemmCall* calls, int n, uint32_t* counters, cudaStream_t stream);
 // true when launch_gemm would pick the CTA-pair kernel (the only one with the fused-norm epilogue)
 bool gemm_uses_cta_pairs(int a_rows, int n_store);
 // encode the descriptors launch_gemm would build for `c` into tmap_a_out / tmap_b_out
