@@ -373,6 +373,9 @@ def run_ours(args):
     if args.no_pdl:
         from tts_max_b200 import _lib
         _lib.check(_lib.load().b200codec_set_pdl(0))
+    if args.no_early_weights:
+        from tts_max_b200 import _lib
+        _lib.check(_lib.load().b200codec_set_gemm_early_weights(0))
     if args.chain:
         from tts_max_b200 import _lib
         _lib.check(_lib.load().b200codec_set_gemm_chain(1))
@@ -641,6 +644,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the config-3 strong-scaling block")
     ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 / config-1 latency block")
+    ap.add_argument("--no-early-weights", action="store_true", help="A/B: GEMM weight loads only after griddepcontrol.wait")
     ap.add_argument("--chain", action="store_true", help="A/B: per-block GEMM chains (one persistent launch for c_proj -> fc1 -> fc2 -> next c_attn)")
     ap.add_argument("--istft-tile", type=int, default=0, help="A/B: output hops per ISTFT CTA (12 or 28)")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: plain stream-ordered launches instead of programmatic dependent launch")

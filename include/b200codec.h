@@ -169,6 +169,13 @@ int b200codec_set_frontend_fold(int mode);
  * times as many. Every output element sees the same K order, so results are bit-identical. A/B switch. */
 int b200codec_set_gemm_narrow_tiles(int on);
 
+/* Default on: a GEMM launch issues the WEIGHT halves of its first pipeline stages before
+ * griddepcontrol.wait (weights are never written by a kernel of the decode), so their DRAM latency overlaps
+ * the predecessor's tail; the activation halves follow after the wait. b200codec_gemm callers whose `w_dev`
+ * is produced by the kernel directly before on the same stream WITH programmatic dependent launch must
+ * switch this off. A/B switch. */
+int b200codec_set_gemm_early_weights(int on);
+
 /* GEMM chains (default OFF): c_proj -> fc1 -> fc2 -> the next block's c_attn of every transformer block run
  * as one persistent launch whose tiles wait for the 256-row block they read (csrc/gemm_tc05_2cta.cuh)
  * instead of four launches that each drain the grid. Same arithmetic per element. Measured: no faster than
@@ -248,6 +255,40 @@ int b200codec_groupnorm_swish(int precision, const float* x_dev, const float* ga
  * qkv [sum(T), 3*H*64] operand dtype, rows "(r h d)"; out [sum(T), H*64]. */
 int b200codec_attention(int precision, const void* qkv_dev, const int32_t* seqlens_host,
                         int n_utts, int heads, void* out_dev, void* stream);
+
+/* ---- encode direction ------------------------------------------------------------------
+ * Replaces tts.core.codec.encoder.Encoder.forward (tts/core/codec/encoder.py:58-78) minus the w2v-BERT model:
+ * AcousticEncoder (encoder_modules.py:128-191: weight-normed Conv1d stack with dilations 1/3/9, strides
+ * 2/2/4/4/5, Activation1d(SnakeBeta) -- activations.py:47-110, filters.py:87-135), SemanticEncoder
+ * (encoder_modules.py:72-125), fusion_layer (encoder.py:42,69) and ResidualFSQ.forward (encoder.py:73-78).
+ * The handle takes the keys of Encoder.state_dict() (`semantic_encoder.*`, `acoustic_encoder.*`,
+ * `fusion_layer.*`, `quantizer.project_{in,out}.*`); the two checkpoint layouts of
+ * Encoder.load_from_checkpoint (encoder.py:80-112) stay in Python. Same conventions as above: 0 on success,
+ * b200codec_last_error() for the message, no CPU fallback, one encode at a time per handle (mutex). */
+typedef struct B200Enc B200Enc;
+int b200enc_create(int precision, int device, B200Enc** out);
+void b200enc_destroy(B200Enc* h);
+int b200enc_num_tensors(const B200Enc* h);
+const char* b200enc_tensor_key(const B200Enc* h, int i);
+int b200enc_tensor_shape(const B200Enc* h, int i, int64_t shape_out[4]);
+/* fp32 host tensor for one state-dict key (strict: unknown keys and shape mismatches fail) */
+int b200enc_load_tensor(B200Enc* h, const char* key, const float* host_ptr, const int64_t* shape, int ndim);
+/* folds weight_norm (g * v / ||v||), lays the strided convs out per super-row, casts to the operand dtype */
+int b200enc_finalize_weights(B200Enc* h, void* stream);
+/* ONE utterance: wav_dev [n_samples] fp32 with n_samples a positive multiple of 320 (Encoder.encode pads to
+ * that, encoder.py:116-120); w2v_dev [T][1024] fp32 = the w2v-BERT `hidden_states[16]` of the same audio,
+ * T = n_samples / 320. Writes ids [T] (id_type 0: int32 like the reference, 1: int64; NULL: skip) and, when
+ * non-NULL, hidden_dev [T][2048], acoustic_dev [T][1024], semantic_dev [T][1024] (fp32, token-major).
+ * pre_bound: see b200codec_fsq_quantize. Asynchronous on `stream`. */
+int b200enc_encode(B200Enc* h, const float* wav_dev, int64_t n_samples, const float* w2v_dev, void* ids_dev,
+                   int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev, float* semantic_dev,
+                   void* stream);
+/* stage parity: with taps on, every encode keeps conv_blocks[0 .. 5] outputs ("conv0", "block1" .. "block5");
+ * read_stage returns one as fp32 token-major [rows][C] (rows = n_samples / stride so far, C = 48 * 2^i) */
+int b200enc_set_stage_taps(B200Enc* h, int on);
+int b200enc_read_stage(B200Enc* h, const char* name, int64_t n_samples, float* host_out, size_t n_elems,
+                       void* stream);
+int64_t b200enc_launch_count(const B200Enc* h);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "b200codec.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200codec_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(b200(?:codec|enc)_\w+)\s*\(", text)))
 
 
 def test_library_is_built_in_tree():

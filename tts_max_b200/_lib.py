@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200codec_set_gemm_narrow_tiles": (c_int, [c_int]),
     "b200codec_set_istft_tile": (c_int, [c_int]),
     "b200codec_set_gemm_chain": (c_int, [c_int]),
+    "b200codec_set_gemm_early_weights": (c_int, [c_int]),
     "b200codec_set_frontend_fold": (c_int, [c_int]),
     "b200codec_set_pdl": (c_int, [c_int]),
     "b200codec_samples_per_token": (c_int, [c_void_p]),
@@ -76,6 +77,19 @@ SIGNATURES = {
     "b200codec_groupnorm_swish": (c_int, [c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int,
                                           c_float, c_void_p, c_void_p]),
     "b200codec_attention": (c_int, [c_int, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p, c_void_p]),
+    # encode direction (b200enc_*)
+    "b200enc_create": (c_int, [c_int, c_int, POINTER(c_void_p)]),
+    "b200enc_destroy": (None, [c_void_p]),
+    "b200enc_num_tensors": (c_int, [c_void_p]),
+    "b200enc_tensor_key": (c_char_p, [c_void_p, c_int]),
+    "b200enc_tensor_shape": (c_int, [c_void_p, c_int, POINTER(c_int64)]),
+    "b200enc_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    "b200enc_finalize_weights": (c_int, [c_void_p, c_void_p]),
+    "b200enc_encode": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "b200enc_set_stage_taps": (c_int, [c_void_p, c_int]),
+    "b200enc_read_stage": (c_int, [c_void_p, c_char_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "b200enc_launch_count": (c_int64, [c_void_p]),
 }
 
 _lib = None

@@ -25,6 +25,7 @@
 
 namespace b200 {
 extern int g_gemm_narrow_tiles;  // gemm_tc05.cu: 256 x 64 tiles for small M (default on)
+extern int g_gemm_early_weights;  // gemm_tc05.cu: weight loads before griddepcontrol.wait (default on)
 
 int g_use_pdl = 1;
 // ids -> embed output: 1 = folded, im2col of the codes + one K = 128 tensor-core GEMM (default);
@@ -1649,6 +1650,11 @@ int b200codec_set_frontend_fold(int mode) {
     B200_CHECK(mode >= 0 && mode <= 2, "front-end mode must be 0 (lookup + conv7 GEMM), 1 (folded, tensor cores) "
                                        "or 2 (folded, fp32 FMA kernel)");
     g_frontend_fold = mode;
+    return 0;
+}
+
+int b200codec_set_gemm_early_weights(int on) {
+    g_gemm_early_weights = on != 0;
     return 0;
 }
 

@@ -1,0 +1,802 @@
+// b200enc: the ENCODE direction up to the FSQ ids -- AcousticEncoder, SemanticEncoder,
+// fusion layer and quantise of tts/core/codec/encoder.py:58-78; the w2v-BERT model that produces the semantic
+// features stays in HuggingFace and its hidden state is an input.
+//
+// Replaces (reference, all ATen there):
+//   AcousticEncoder.forward        tts/core/codec/encoder_modules.py:128-191
+//     ResidualUnit / EncoderBlock   :20-69   (weight-normed Conv1d k = 7 dilated 1/3/9, k = 1, k = 2s stride s)
+//     Activation1d(SnakeBeta)       tts/core/codec/activations.py:47-110, filters.py:87-135
+//   SemanticEncoder.forward        tts/core/codec/encoder_modules.py:72-125
+//   fusion_layer, Encoder.quantize tts/core/codec/encoder.py:42, 66-78
+//
+// B200 mapping. Activations are token-major (channels-last) [rows, C] like the decoder's, C padded to a multiple
+// of 64 (48 -> 64, 96 -> 128; pad channels stay exactly zero), one utterance per launch sequence:
+//   * every Conv1d is the tcgen05 GEMM of gemm_tc05*.cuh: k = 7 dilated = 7 row-shifted K-slabs with a row
+//     stride of `dilation` (zero padding = TMA out-of-bounds fill at the array ends); the strided
+//     down-sampling conv (k = 2s, stride s) is a 3-tap conv over the SAME buffer viewed as [rows / s, s * C]
+//     with the kernel laid out (and zero-filled) per super-row at load time; weight-norm is folded at load;
+//   * Activation1d (2x FIR up-sampling, SnakeBeta, 2x FIR down-sampling, replicate padding) is one fused
+//     CUDA-core kernel: fp32 in, 16-bit GEMM operand out, nothing at the doubled rate ever reaches memory;
+//   * bias / ReLU / residual adds ride the GEMM epilogues; the fusion Linear reads the two encoders' 16-bit
+//     outputs from one [T, 2048] buffer they were written into side by side (the concat is free).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200codec.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+namespace {
+
+constexpr int kStages = 5;
+constexpr int kStrides[kStages] = {2, 2, 4, 4, 5};
+constexpr int kDil[3] = {1, 3, 9};
+constexpr int kGenFeatures = 48;
+constexpr int kOutDim = 1024;
+constexpr int kHopTotal = 320;
+
+inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        B200_CUDA_OK(cudaMalloc(&p, need + need / 4));
+        bytes = need + need / 4;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+// conv_blocks[0]: Conv1d(1 -> 48, k = 7, padding 3), weight-normed: x0[t, c] = b[c] + sum_k w[c][k] wav[t + k - 3]
+__global__ void __launch_bounds__(256)
+enc_conv0_kernel(const float* __restrict__ wav, int S, const float* __restrict__ w /*[C][7]*/,
+                 const float* __restrict__ bias, int C, int P, float* __restrict__ out /*[S][P]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int c = threadIdx.x % P;  // blockDim.x is a multiple of P
+    const int rows_per_block = blockDim.x / P;
+    const int t = blockIdx.x * rows_per_block + threadIdx.x / P;
+    if (t >= S) return;
+    float acc = 0.f;
+    if (c < C) {
+        acc = bias[c];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int i = t + k - 3;
+            if (i >= 0 && i < S) acc = fmaf(w[c * 7 + k], __ldg(wav + i), acc);
+        }
+    }
+    out[static_cast<size_t>(t) * P + c] = acc;
+}
+
+// Activation1d(SnakeBeta) fused (activations.py:90-110, filters.py:87-135 with ratio 2, 12-tap kaiser-sinc
+// filters, replicate padding):
+//   u[2t]   = 2 sum_j fu[2j+1] x[t+2-j]       u[2t+1] = 2 sum_j fu[2j] x[t+3-j]      (j = 0..5, rows clamped)
+//   s[n]    = u[n] + sin^2(u[n] e^alpha) / (e^beta + 1e-9)                           (n in [0, 2T))
+//   y[t]    = sum_k fd[k] s[clamp(2t + k - 5, 0, 2T - 1)]                            (k = 0..11)
+// A thread owns one channel and kSnakeRows consecutive rows: the 2 * rows + 10 snake values it needs live in
+// registers, consecutive threads are consecutive channels (coalesced 128-byte row segments).
+constexpr int kSnakeRows = 16;
+
+struct SnakeFilters {
+    float up[12];
+    float down[12];
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restrict__ alpha /*[P] e^alpha*/,
+                const float* __restrict__ inv_beta /*[P] 1 / (e^beta + 1e-9)*/, SnakeFilters f,
+                OutT* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int K = kSnakeRows;
+    const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int t0 = (blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6)) * K;
+    if (t0 >= T || c >= P) return;
+    const float a = alpha[c], ib = inv_beta[c];
+    auto snake = [&](float u) {
+        // sin via MUFU after a two-term Cody-Waite reduction of the argument to [-pi, pi]
+        const float z = u * a;
+        const float kq = rintf(z * 0.15915494309189535f);
+        float r = fmaf(kq, -6.2831854820251465f, z);
+        r = fmaf(kq, 1.7484556000744487e-07f, r);
+        const float sn = __sinf(r);
+        return fmaf(sn * sn, ib, u);
+    };
+    // rows t0 - 6 .. t0 + K + 5 (clamped)
+    float xr[K + 12];
+#pragma unroll
+    for (int r = 0; r < K + 12; ++r) {
+        const int t = min(max(t0 - 6 + r, 0), T - 1);
+        xr[r] = __ldg(x + static_cast<size_t>(t) * P + c);
+    }
+    // s[n] for n = 2 t0 - 5 + q, q = 0 .. 2K + 9; row t = t0 - 3 + (q + 1) / 2 for odd n (q even), t0 - 2 + q / 2 ...
+    float sv[2 * K + 10];
+#pragma unroll
+    for (int q = 0; q < 2 * K + 10; ++q) {
+        // n = 2 t0 - 5 + q. q odd -> n even = 2 t with t = t0 - 2 + (q - 1) / 2; q even -> n odd = 2 t + 1 with
+        // t = t0 - 3 + q / 2. xr index of row t + d is (t - t0 + 6 + d).
+        float u = 0.f;
+        if (q & 1) {
+            const int tr = 4 + (q - 1) / 2;  // xr index of row t
+#pragma unroll
+            for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j + 1], xr[tr + 2 - j], u);
+        } else {
+            const int tr = 3 + q / 2;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j], xr[tr + 3 - j], u);
+        }
+        sv[q] = snake(2.f * u);
+    }
+    // replicate padding of the UP-SAMPLED signal at the two ends of the utterance (warp-uniform branches)
+    if (2 * t0 - 5 < 0) {
+        float u = 0.f;  // s[0]: n = 0 = 2 * 0, rows 2, 1, 0, -1, -2, -3 clamped
+#pragma unroll
+        for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j + 1], __ldg(x + static_cast<size_t>(min(max(2 - j, 0), T - 1)) * P + c), u);
+        const float s0 = snake(2.f * u);
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (2 * t0 - 5 + q < 0) sv[q] = s0;
+    }
+    if (2 * t0 + 2 * K + 4 > 2 * T - 1) {
+        float u = 0.f;  // s[2T - 1]: n odd = 2 (T - 1) + 1, rows T+2, T+1, T, T-1, T-2, T-3 clamped
+#pragma unroll
+        for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j], __ldg(x + static_cast<size_t>(min(max(T - 1 + 3 - j, 0), T - 1)) * P + c), u);
+        const float sl = snake(2.f * u);
+#pragma unroll
+        for (int q = 0; q < 2 * K + 10; ++q)
+            if (2 * t0 - 5 + q > 2 * T - 1) sv[q] = sl;
+    }
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        if (t0 + r >= T) break;
+        float y = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) y = fmaf(f.down[k], sv[2 * r + k], y);
+        out[static_cast<size_t>(t0 + r) * P + c] = Half16<OutT>::from_float(y);
+    }
+}
+
+template <typename OutT>
+__global__ void cast_kernel(const float* __restrict__ x, size_t n, OutT* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = Half16<OutT>::from_float(x[i]);
+}
+
+// weight-normed Conv1d weight [Cout][Cin][k] (scale[Cout] = g / ||v||) -> GEMM operand [Npad][k * Cinpad], zero padded
+template <typename T>
+__global__ void enc_repack_conv_kernel(const float* __restrict__ v, const float* __restrict__ scale, T* __restrict__ dst,
+                                       int Cout, int Cin, int k, int Npad, int Cinpad) {
+    const size_t total = static_cast<size_t>(Npad) * k * Cinpad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cinpad);
+        const size_t rest = i / Cinpad;
+        const int tap = static_cast<int>(rest % k);
+        const int n = static_cast<int>(rest / k);
+        float w = 0.f;
+        if (n < Cout && c < Cin) w = v[(static_cast<size_t>(n) * Cin + c) * k + tap] * (scale ? scale[n] : 1.f);
+        dst[i] = Half16<T>::from_float(w);
+    }
+}
+
+// strided conv (k = 2s, stride s, padding p) as a 3-tap conv over super-rows of s input rows:
+// dst[n][(tap' * s + r) * Cinpad + c] = w[n][c][s (tap' - 1) + r + p] when that kernel index exists, else 0
+template <typename T>
+__global__ void enc_repack_strided_kernel(const float* __restrict__ v, const float* __restrict__ scale, T* __restrict__ dst,
+                                          int Cout, int Cin, int s, int p, int Npad, int Cinpad) {
+    const int k = 2 * s;
+    const size_t total = static_cast<size_t>(Npad) * 3 * s * Cinpad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cinpad);
+        size_t rest = i / Cinpad;
+        const int r = static_cast<int>(rest % s);
+        rest /= s;
+        const int tp = static_cast<int>(rest % 3);
+        const int n = static_cast<int>(rest / 3);
+        const int kk = s * (tp - 1) + r + p;
+        float w = 0.f;
+        if (n < Cout && c < Cin && kk >= 0 && kk < k) w = v[(static_cast<size_t>(n) * Cin + c) * k + kk] * scale[n];
+        dst[i] = Half16<T>::from_float(w);
+    }
+}
+
+__global__ void enc_pad_vec_kernel(const float* __restrict__ src, int n, int npad, int mode, float* __restrict__ dst) {
+    // mode 0: copy, zero pad; 1: exp(src), pad exp(0) = 1; 2: 1 / (exp(src) + 1e-9), pad 1 / (1 + 1e-9)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    const float v = i < n ? src[i] : 0.f;
+    dst[i] = mode == 0 ? (i < n ? v : 0.f) : mode == 1 ? expf(v) : 1.f / (expf(v) + 1e-9f);
+}
+
+struct TensorSpec {
+    std::string key;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto d : shape) n *= static_cast<size_t>(d);
+        return n;
+    }
+};
+
+struct ActW {           // Activation1d(SnakeBeta)
+    float* alpha = nullptr;     // [P] e^alpha
+    float* inv_beta = nullptr;  // [P] 1 / (e^beta + 1e-9)
+    SnakeFilters f;
+};
+struct ConvW {
+    void* w = nullptr;          // operand dtype [Npad][K]
+    float* bias = nullptr;      // [Npad]
+};
+struct UnitW {
+    ActW act0, act2;
+    ConvW conv7, conv1;
+};
+struct StageW {
+    UnitW unit[3];
+    ActW act;
+    ConvW down;
+};
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+struct B200Enc {
+    int precision = 0, device = 0;
+    std::vector<TensorSpec> specs;
+    std::map<std::string, int> index;
+    std::vector<float*> master;
+    bool finalized = false;
+    std::mutex mu;
+
+    Buf wbuf;  // operand-dtype weights
+    Buf fbuf;  // fp32 vectors (padded biases, exp(alpha), 1 / exp(beta))
+    float* conv0_w = nullptr;
+    float* conv0_b = nullptr;
+    StageW stage[kStages];
+    ActW act_final;
+    ConvW conv_final;
+    ConvW sem_init, sem_rb1, sem_rb3, sem_final, fusion;
+
+    // workspace for one utterance of up to ws_samples samples
+    Buf ws;
+    int64_t ws_samples = 0;
+    float* x[kStages + 1];   // fp32 [R_i][P_i]
+    float* hb[kStages];      // fp32 conv7 output
+    void* a[kStages + 1];    // operand [R_i][P_i]
+    void *s16a, *s16b;       // semantic encoder operands [T][1024]
+    float *sr, *sx;          // semantic fp32 [T][1024]
+    void* cat16;             // [T][2048] operand: [semantic | acoustic]
+    float *ac32, *sem32, *hid32;  // fp32 [T][1024], [T][1024], [T][2048]
+
+    int64_t launches = 0;
+    // debug taps (b200enc_set_stage_taps): copies of conv_blocks[0 .. 5] outputs taken when they are produced
+    // (the residual units update x[i] in place afterwards)
+    bool taps_on = false;
+    Buf tap[kStages + 1];
+    int64_t tap_samples = 0;
+
+    const float* m(const std::string& key) const {
+        auto it = index.find(key);
+        return it == index.end() ? nullptr : master[it->second];
+    }
+};
+
+namespace {
+
+void add_spec(B200Enc* h, const std::string& key, std::vector<int64_t> shape) {
+    h->index[key] = static_cast<int>(h->specs.size());
+    h->specs.push_back({key, std::move(shape)});
+}
+
+// Encoder.state_dict() keys (encoder.py:28-44) in module order: semantic_encoder, acoustic_encoder,
+// fusion_layer, quantizer (project_in / project_out are the only persistent tensors of ResidualFSQ)
+void build_specs(B200Enc* h) {
+    const std::string s = "semantic_encoder.";
+    add_spec(h, s + "initial_conv.weight", {1024, 1024, 3});
+    add_spec(h, s + "residual_blocks.1.weight", {1024, 1024, 3});
+    add_spec(h, s + "residual_blocks.1.bias", {1024});
+    add_spec(h, s + "residual_blocks.3.weight", {1024, 1024, 3});
+    add_spec(h, s + "residual_blocks.3.bias", {1024});
+    add_spec(h, s + "final_conv.weight", {1024, 1024, 3});
+    auto act = [&](const std::string& p, int64_t c) {
+        add_spec(h, p + "act.alpha", {c});
+        add_spec(h, p + "act.beta", {c});
+        add_spec(h, p + "upsample.filter", {1, 1, 12});
+        add_spec(h, p + "downsample.lowpass.filter", {1, 1, 12});
+    };
+    auto wn = [&](const std::string& p, int64_t cout, int64_t cin, int64_t k) {
+        add_spec(h, p + "bias", {cout});
+        add_spec(h, p + "weight_g", {cout, 1, 1});
+        add_spec(h, p + "weight_v", {cout, cin, k});
+    };
+    const std::string a = "acoustic_encoder.";
+    wn(a + "conv_blocks.0.", kGenFeatures, 1, 7);
+    int64_t d = kGenFeatures;
+    for (int i = 0; i < kStages; ++i) {
+        const std::string p = a + "conv_blocks." + std::to_string(i + 1) + ".";
+        for (int u = 0; u < 3; ++u) {
+            const std::string q = p + "block." + std::to_string(u) + ".";
+            act(q + "block.0.", d);
+            wn(q + "block.1.", d, d, 7);
+            act(q + "block.2.", d);
+            wn(q + "block.3.", d, d, 1);
+        }
+        act(p + "block.3.", d);
+        wn(p + "block.4.", 2 * d, d, 2 * kStrides[i]);
+        d *= 2;
+    }
+    act(a + "conv_final_block.0.", d);
+    wn(a + "conv_final_block.1.", kOutDim, d, 3);
+    add_spec(h, "fusion_layer.weight", {2048, 2048});
+    add_spec(h, "fusion_layer.bias", {2048});
+    add_spec(h, "quantizer.project_in.weight", {8, 2048});
+    add_spec(h, "quantizer.project_in.bias", {8});
+    add_spec(h, "quantizer.project_out.weight", {2048, 8});
+    add_spec(h, "quantizer.project_out.bias", {2048});
+}
+
+#define ENC_RUN(expr)              \
+    do {                           \
+        if ((expr) != 0) return 1; \
+        h->launches++;             \
+    } while (0)
+
+template <typename T>
+int repack_conv(const float* v, const float* scale, void* dst, int Cout, int Cin, int k, int Npad, int Cinpad, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(Npad) * k * Cinpad;
+    const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, 8192));
+    enc_repack_conv_kernel<T><<<grid, 256, 0, s>>>(v, scale, static_cast<T*>(dst), Cout, Cin, k, Npad, Cinpad);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+template <typename T>
+int repack_strided(const float* v, const float* scale, void* dst, int Cout, int Cin, int st, int p, int Npad, int Cinpad,
+                   cudaStream_t s) {
+    const size_t total = static_cast<size_t>(Npad) * 3 * st * Cinpad;
+    const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, 8192));
+    enc_repack_strided_kernel<T><<<grid, 256, 0, s>>>(v, scale, static_cast<T*>(dst), Cout, Cin, st, p, Npad, Cinpad);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int snake(B200Enc* h, const float* x, int T, int P, const ActW& w, void* out, cudaStream_t s) {
+    const int row_groups = 256 / 64;  // 4 row chunks per CTA
+    dim3 grid((T + kSnakeRows * row_groups - 1) / (kSnakeRows * row_groups), P / 64);
+    if (h->precision == kPrecBf16)
+        B200_CUDA_OK(launch_kernel(snake_aa_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, x, T, P, w.alpha, w.inv_beta, w.f,
+                                   static_cast<__nv_bfloat16*>(out)));
+    else
+        B200_CUDA_OK(launch_kernel(snake_aa_kernel<__half>, grid, dim3(256), 0, s, x, T, P, w.alpha, w.inv_beta, w.f,
+                                   static_cast<__half*>(out)));
+    return 0;
+}
+
+GemmCall conv_call(B200Enc* h, const void* a, int rows, int Cin, const ConvW& w, int N, int taps, int dil, void* out,
+                   bool out_fp32, int ldc, const float* residual, int act) {
+    GemmCall c{};
+    c.precision = h->precision;
+    c.a = a;
+    c.a_rows = rows;
+    c.Cin = Cin;
+    c.w = w.w;
+    c.N = N;
+    c.taps = taps;
+    c.tap_pad = -1;
+    c.tap_dil = dil;
+    c.out = out;
+    c.out_fp32 = out_fp32 ? 1 : 0;
+    c.ldc = ldc;
+    c.n_store = N;
+    c.bias = w.bias;
+    c.residual = residual;
+    c.ld_res = ldc;
+    c.row_valid = nullptr;
+    c.act = act;
+    c.out16_scale = 1.f;
+    c.ss_in_scale = 1.f;
+    return c;
+}
+
+int ensure_ws(B200Enc* h, int64_t S) {
+    if (S <= h->ws_samples) return 0;
+    const size_t es = 2;
+    const int64_t T = S / kHopTotal;
+    auto al = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
+    size_t total = 0;
+    int64_t rows = S;
+    int c = kGenFeatures;
+    size_t off_x[kStages + 1], off_h[kStages], off_a[kStages + 1];
+    for (int i = 0; i <= kStages; ++i) {
+        const size_t P = pad64(c);
+        off_x[i] = total; total += al(static_cast<size_t>(rows) * P * 4);
+        if (i < kStages) { off_h[i] = total; total += al(static_cast<size_t>(rows) * P * 4); }
+        off_a[i] = total; total += al(static_cast<size_t>(rows) * P * es);
+        if (i < kStages) { rows /= kStrides[i]; c *= 2; }
+    }
+    const size_t sz16 = al(static_cast<size_t>(T) * 1024 * es), sz32 = al(static_cast<size_t>(T) * 1024 * 4);
+    const size_t o_s16a = total; total += sz16;
+    const size_t o_s16b = total; total += sz16;
+    const size_t o_sr = total; total += sz32;
+    const size_t o_sx = total; total += sz32;
+    const size_t o_cat = total; total += 2 * sz16;
+    const size_t o_ac = total; total += sz32;
+    const size_t o_sem = total; total += sz32;
+    const size_t o_hid = total; total += 2 * sz32;
+    h->ws_samples = 0;
+    if (h->ws.ensure(total)) return 1;
+    B200_CUDA_OK(cudaMemset(h->ws.p, 0, h->ws.bytes));
+    uint8_t* p = static_cast<uint8_t*>(h->ws.p);
+    for (int i = 0; i <= kStages; ++i) {
+        h->x[i] = reinterpret_cast<float*>(p + off_x[i]);
+        if (i < kStages) h->hb[i] = reinterpret_cast<float*>(p + off_h[i]);
+        h->a[i] = p + off_a[i];
+    }
+    h->s16a = p + o_s16a; h->s16b = p + o_s16b;
+    h->sr = reinterpret_cast<float*>(p + o_sr); h->sx = reinterpret_cast<float*>(p + o_sx);
+    h->cat16 = p + o_cat;
+    h->ac32 = reinterpret_cast<float*>(p + o_ac); h->sem32 = reinterpret_cast<float*>(p + o_sem);
+    h->hid32 = reinterpret_cast<float*>(p + o_hid);
+    // the workspace is sized for (S + S / 4) samples by Buf::ensure's slack only in bytes; rows are bounded by S
+    h->ws_samples = S;
+    return 0;
+}
+
+struct EncTap {
+    std::string name;
+    const float* ptr;
+    int64_t rows;
+    int C, P;
+};
+
+}  // namespace
+
+extern "C" {
+
+int b200enc_create(int precision, int device, B200Enc** out) {
+    B200_CHECK(out != nullptr, "b200enc_create: null argument");
+    B200_CHECK(precision == B200CODEC_BF16 || precision == B200CODEC_FP16, "precision %d is not available (bf16 = 0, fp16 = 1)",
+               precision);
+    int ndev = 0;
+    B200_CUDA_OK(cudaGetDeviceCount(&ndev));
+    B200_CHECK(device >= 0 && device < ndev, "CUDA device %d not present (%d devices); this library has no CPU fallback", device, ndev);
+    cudaDeviceProp prop;
+    B200_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    B200_CHECK(prop.major == 10, "device %d is sm_%d%d; b200codec kernels are built for sm_100a only", device, prop.major, prop.minor);
+    B200Enc* h = new B200Enc();
+    h->precision = precision;
+    h->device = device;
+    build_specs(h);
+    h->master.assign(h->specs.size(), nullptr);
+    *out = h;
+    return 0;
+}
+
+void b200enc_destroy(B200Enc* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (float* p : h->master)
+        if (p) cudaFree(p);
+    h->wbuf.release();
+    h->fbuf.release();
+    h->ws.release();
+    for (auto& t : h->tap) t.release();
+    delete h;
+}
+
+int b200enc_num_tensors(const B200Enc* h) { return h ? static_cast<int>(h->specs.size()) : 0; }
+const char* b200enc_tensor_key(const B200Enc* h, int i) {
+    if (!h || i < 0 || i >= static_cast<int>(h->specs.size())) return nullptr;
+    return h->specs[i].key.c_str();
+}
+int b200enc_tensor_shape(const B200Enc* h, int i, int64_t shape_out[4]) {
+    if (!h || i < 0 || i >= static_cast<int>(h->specs.size())) return -1;
+    const auto& s = h->specs[i].shape;
+    for (size_t d = 0; d < s.size() && d < 4; ++d) shape_out[d] = s[d];
+    return static_cast<int>(s.size());
+}
+
+int b200enc_load_tensor(B200Enc* h, const char* key, const float* host_ptr, const int64_t* shape, int ndim) {
+    B200_CHECK(h && key && host_ptr && shape, "b200enc_load_tensor: null argument");
+    auto it = h->index.find(key);
+    B200_CHECK(it != h->index.end(), "Unexpected key(s) in state_dict: \"%s\"", key);
+    const TensorSpec& sp = h->specs[it->second];
+    bool ok = static_cast<int>(sp.shape.size()) == ndim;
+    for (int d = 0; ok && d < ndim; ++d) ok = sp.shape[d] == shape[d];
+    B200_CHECK(ok, "size mismatch for %s: checkpoint tensor does not match the model shape", key);
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    float*& dst = h->master[it->second];
+    if (dst == nullptr) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dst), sp.numel() * sizeof(float)));
+    B200_CUDA_OK(cudaMemcpy(dst, host_ptr, sp.numel() * sizeof(float), cudaMemcpyHostToDevice));
+    h->finalized = false;
+    return 0;
+}
+
+int b200enc_finalize_weights(B200Enc* h, void* stream) {
+    B200_CHECK(h != nullptr, "null handle");
+    if (h->finalized) return 0;
+    std::lock_guard<std::mutex> lock(h->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    std::string missing;
+    for (size_t i = 0; i < h->specs.size(); ++i)
+        if (h->master[i] == nullptr && missing.size() < 600) missing += (missing.empty() ? "\"" : ", \"") + h->specs[i].key + "\"";
+    B200_CHECK(missing.empty(), "Missing key(s) in state_dict: %s", missing.c_str());
+
+    // sizes
+    size_t welems = 0, felems = 2 * 64 + 7 * 64;
+    {
+        int c = kGenFeatures;
+        for (int i = 0; i < kStages; ++i) {
+            const size_t P = pad64(c), P2 = pad64(2 * c);
+            welems += 3 * (P * 7 * P + P * P) + P2 * 3 * kStrides[i] * P + 8 * 256;
+            felems += 3 * (2 * P + 2 * P + 2 * P) + 2 * P + P2 + 64;
+            c *= 2;
+        }
+        welems += static_cast<size_t>(kOutDim) * 3 * pad64(c) + 4ull * 1024 * 3 * 1024 + 2048ull * 2048 + 16 * 256;
+        felems += 2 * pad64(c) + kOutDim + 4 * 1024 + 2048 + 64;
+    }
+    if (h->wbuf.ensure(welems * 2 + 64 * 1024)) return 1;
+    (void)felems;
+    if (h->fbuf.ensure(static_cast<size_t>(4) << 20)) return 1;  // ~0.2 M floats of padded vectors; 4 MB is ample
+    uint8_t* wp = static_cast<uint8_t*>(h->wbuf.p);
+    float* fp = static_cast<float*>(h->fbuf.p);
+    auto takew = [&](size_t n) { void* r = wp; wp += (n * 2 + 255) & ~static_cast<size_t>(255); return r; };
+    auto takef = [&](size_t n) { float* r = fp; fp += (n + 63) & ~static_cast<size_t>(63); return r; };
+    float* scale = nullptr;
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&scale), 4096 * sizeof(float)));
+    const bool bf = h->precision == kPrecBf16;
+    auto padvec = [&](const float* src, int n, int npad, int mode) -> float* {
+        float* dst = takef(npad);
+        enc_pad_vec_kernel<<<(npad + 255) / 256, 256, 0, s>>>(src, n, npad, mode, dst);
+        return dst;
+    };
+    auto make_act = [&](const std::string& p, int C, ActW* w) -> int {
+        const int P = pad64(C);
+        w->alpha = padvec(h->m(p + "act.alpha"), C, P, 1);
+        w->inv_beta = padvec(h->m(p + "act.beta"), C, P, 2);
+        float fu[12], fd[12];
+        B200_CUDA_OK(cudaMemcpy(fu, h->m(p + "upsample.filter"), sizeof(fu), cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(fd, h->m(p + "downsample.lowpass.filter"), sizeof(fd), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 12; ++i) {
+            w->f.up[i] = fu[i];
+            w->f.down[i] = fd[i];
+        }
+        return 0;
+    };
+    // weight-normed conv: scale = g / ||v||, operand [Npad][k * Cinpad]
+    auto make_wn_conv = [&](const std::string& p, int Cout, int Cin, int k, ConvW* w) -> int {
+        const int Np = pad64(Cout), Cp = pad64(Cin);
+        if (launch_weightnorm_scale(h->m(p + "weight_g"), h->m(p + "weight_v"), Cout, Cin * k, scale, s)) return 1;
+        w->w = takew(static_cast<size_t>(Np) * k * Cp);
+        if (bf ? repack_conv<__nv_bfloat16>(h->m(p + "weight_v"), scale, w->w, Cout, Cin, k, Np, Cp, s)
+               : repack_conv<__half>(h->m(p + "weight_v"), scale, w->w, Cout, Cin, k, Np, Cp, s))
+            return 1;
+        w->bias = padvec(h->m(p + "bias"), Cout, Np, 0);
+        return 0;
+    };
+    auto make_plain_conv = [&](const float* wsrc, const float* bsrc, int Cout, int Cin, int k, ConvW* w) -> int {
+        w->w = takew(static_cast<size_t>(Cout) * k * Cin);
+        if (bf ? repack_conv<__nv_bfloat16>(wsrc, nullptr, w->w, Cout, Cin, k, Cout, Cin, s)
+               : repack_conv<__half>(wsrc, nullptr, w->w, Cout, Cin, k, Cout, Cin, s))
+            return 1;
+        w->bias = bsrc ? padvec(bsrc, Cout, Cout, 0) : nullptr;
+        return 0;
+    };
+    const std::string a = "acoustic_encoder.";
+    {
+        // conv_blocks.0: fp32 FIR weights [48][7] with the weight-norm scale folded on the host
+        std::vector<float> g(kGenFeatures), v(kGenFeatures * 7), w(kGenFeatures * 7);
+        B200_CUDA_OK(cudaMemcpy(g.data(), h->m(a + "conv_blocks.0.weight_g"), g.size() * 4, cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(v.data(), h->m(a + "conv_blocks.0.weight_v"), v.size() * 4, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < kGenFeatures; ++c) {
+            double n2 = 0.0;
+            for (int k = 0; k < 7; ++k) n2 += static_cast<double>(v[c * 7 + k]) * v[c * 7 + k];
+            const float sc = static_cast<float>(g[c] / std::sqrt(n2));
+            for (int k = 0; k < 7; ++k) w[c * 7 + k] = v[c * 7 + k] * sc;
+        }
+        h->conv0_w = takef(w.size());
+        B200_CUDA_OK(cudaMemcpyAsync(h->conv0_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice, s));
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        h->conv0_b = padvec(h->m(a + "conv_blocks.0.bias"), kGenFeatures, 64, 0);
+    }
+    int c = kGenFeatures;
+    for (int i = 0; i < kStages; ++i) {
+        const std::string p = a + "conv_blocks." + std::to_string(i + 1) + ".";
+        StageW& st = h->stage[i];
+        for (int u = 0; u < 3; ++u) {
+            const std::string q = p + "block." + std::to_string(u) + ".";
+            if (make_act(q + "block.0.", c, &st.unit[u].act0)) return 1;
+            if (make_wn_conv(q + "block.1.", c, c, 7, &st.unit[u].conv7)) return 1;
+            if (make_act(q + "block.2.", c, &st.unit[u].act2)) return 1;
+            if (make_wn_conv(q + "block.3.", c, c, 1, &st.unit[u].conv1)) return 1;
+        }
+        if (make_act(p + "block.3.", c, &st.act)) return 1;
+        {
+            const int sdn = kStrides[i], Np = pad64(2 * c), Cp = pad64(c);
+            const std::string q = p + "block.4.";
+            if (launch_weightnorm_scale(h->m(q + "weight_g"), h->m(q + "weight_v"), 2 * c, c * 2 * sdn, scale, s)) return 1;
+            st.down.w = takew(static_cast<size_t>(Np) * 3 * sdn * Cp);
+            const int pd = sdn / 2 + sdn % 2;
+            if (bf ? repack_strided<__nv_bfloat16>(h->m(q + "weight_v"), scale, st.down.w, 2 * c, c, sdn, pd, Np, Cp, s)
+                   : repack_strided<__half>(h->m(q + "weight_v"), scale, st.down.w, 2 * c, c, sdn, pd, Np, Cp, s))
+                return 1;
+            st.down.bias = padvec(h->m(q + "bias"), 2 * c, Np, 0);
+        }
+        c *= 2;
+    }
+    if (make_act(a + "conv_final_block.0.", c, &h->act_final)) return 1;
+    if (make_wn_conv(a + "conv_final_block.1.", kOutDim, c, 3, &h->conv_final)) return 1;
+    const std::string se = "semantic_encoder.";
+    if (make_plain_conv(h->m(se + "initial_conv.weight"), nullptr, 1024, 1024, 3, &h->sem_init)) return 1;
+    if (make_plain_conv(h->m(se + "residual_blocks.1.weight"), h->m(se + "residual_blocks.1.bias"), 1024, 1024, 3, &h->sem_rb1)) return 1;
+    if (make_plain_conv(h->m(se + "residual_blocks.3.weight"), h->m(se + "residual_blocks.3.bias"), 1024, 1024, 3, &h->sem_rb3)) return 1;
+    if (make_plain_conv(h->m(se + "final_conv.weight"), nullptr, 1024, 1024, 3, &h->sem_final)) return 1;
+    if (make_plain_conv(h->m("fusion_layer.weight"), h->m("fusion_layer.bias"), 2048, 2048, 1, &h->fusion)) return 1;
+    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    B200_CUDA_OK(cudaFree(scale));
+    h->finalized = true;
+    return 0;
+}
+
+// Encoder.forward (encoder.py:58-78) for ONE utterance, the w2v-BERT hidden state given:
+//   wav_dev [n_samples] fp32 (n_samples a positive multiple of 320: Encoder.encode pads to that, :116-120),
+//   w2v_dev [T][1024] fp32 token-major, T = n_samples / 320  ->  ids [T].
+// hidden_dev [T][2048] / acoustic_dev [T][1024] / semantic_dev [T][1024] (fp32, optional) receive the fused
+// hidden state and the two encoders' outputs. Asynchronous on `stream`.
+int b200enc_encode(B200Enc* h, const float* wav_dev, int64_t n_samples, const float* w2v_dev, void* ids_dev,
+                   int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev, float* semantic_dev, void* stream) {
+    B200_CHECK(h && wav_dev && w2v_dev, "b200enc_encode: null argument");
+    B200_CHECK(h->finalized, "b200enc_encode called before b200enc_finalize_weights");
+    B200_CHECK(n_samples > 0 && n_samples % kHopTotal == 0 && n_samples < (1ll << 30),
+               "encode: n_samples (%lld) must be a positive multiple of 320", (long long)n_samples);
+    B200_CHECK(ids_dev == nullptr || id_type == 0 || id_type == 1, "encode: id_type must be 0 (int32) or 1 (int64)");
+    std::lock_guard<std::mutex> lock(h->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    if (n_samples > h->ws_samples) {
+        B200_CUDA_OK(cudaStreamSynchronize(s));  // the old workspace may still be in use
+        if (ensure_ws(h, n_samples)) return 1;
+    }
+    const int S = static_cast<int>(n_samples), T = S / kHopTotal;
+    const bool bf = h->precision == kPrecBf16;
+
+    // ---- acoustic encoder ----
+    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 3) / 4), dim3(256), 0, s, wav_dev, S, (const float*)h->conv0_w,
+                               (const float*)h->conv0_b, kGenFeatures, 64, h->x[0]));
+    h->launches++;
+    auto take_tap = [&](int idx, int64_t r, int Pc) -> int {
+        if (!h->taps_on) return 0;
+        const size_t bytes = static_cast<size_t>(r) * Pc * 4;
+        if (h->tap[idx].ensure(bytes)) return 1;
+        B200_CUDA_OK(cudaMemcpyAsync(h->tap[idx].p, h->x[idx], bytes, cudaMemcpyDeviceToDevice, s));
+        h->tap_samples = n_samples;
+        return 0;
+    };
+    if (take_tap(0, S, 64)) return 1;
+    int rows = S, c = kGenFeatures;
+    for (int i = 0; i < kStages; ++i) {
+        const StageW& st = h->stage[i];
+        const int P = pad64(c);
+        for (int u = 0; u < 3; ++u) {
+            ENC_RUN(snake(h, h->x[i], rows, P, st.unit[u].act0, h->a[i], s));
+            ENC_RUN(launch_gemm(conv_call(h, h->a[i], rows, P, st.unit[u].conv7, P, 7, kDil[u], h->hb[i], true, P, nullptr, kActNone), s));
+            ENC_RUN(snake(h, h->hb[i], rows, P, st.unit[u].act2, h->a[i], s));
+            ENC_RUN(launch_gemm(conv_call(h, h->a[i], rows, P, st.unit[u].conv1, P, 1, 1, h->x[i], true, P, h->x[i], kActNone), s));
+        }
+        ENC_RUN(snake(h, h->x[i], rows, P, st.act, h->a[i], s));
+        const int sdn = kStrides[i], P2 = pad64(2 * c);
+        // the same operand buffer viewed as [rows / s][s * P]: a 3-tap conv over super-rows
+        ENC_RUN(launch_gemm(conv_call(h, h->a[i], rows / sdn, sdn * P, st.down, P2, 3, 1, h->x[i + 1], true, P2, nullptr, kActNone), s));
+        rows /= sdn;
+        c *= 2;
+        if (take_tap(i + 1, rows, P2)) return 1;
+    }
+    const size_t es = 2;
+    {
+        const int P = pad64(c);  // 1536
+        ENC_RUN(snake(h, h->x[kStages], rows, P, h->act_final, h->a[kStages], s));
+        GemmCall g = conv_call(h, h->a[kStages], rows, P, h->conv_final, kOutDim, 3, 1, h->ac32, true, kOutDim, nullptr, kActNone);
+        g.out16 = static_cast<uint8_t*>(h->cat16) + 1024 * es;  // right half of [semantic | acoustic]
+        g.ld16 = 2048;
+        ENC_RUN(launch_gemm(g, s));
+    }
+    // ---- semantic encoder (encoder_modules.py:121-125; ReLU(inplace=True) makes the skip carry relu(x)) ----
+    {
+        const size_t n = static_cast<size_t>(T) * 1024;
+        const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
+        if (bf) B200_CUDA_OK(launch_kernel(cast_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, w2v_dev, n, static_cast<__nv_bfloat16*>(h->s16a)));
+        else B200_CUDA_OK(launch_kernel(cast_kernel<__half>, dim3(grid), dim3(256), 0, s, w2v_dev, n, static_cast<__half*>(h->s16a)));
+        h->launches++;
+        GemmCall g0 = conv_call(h, h->s16a, T, 1024, h->sem_init, 1024, 3, 1, h->sr, true, 1024, nullptr, kActRelu);
+        g0.out16 = h->s16b;  // r = relu(initial_conv(x)) as fp32 (skip) and as operand
+        g0.ld16 = 1024;
+        ENC_RUN(launch_gemm(g0, s));
+        ENC_RUN(launch_gemm(conv_call(h, h->s16b, T, 1024, h->sem_rb1, 1024, 3, 1, h->s16a, false, 1024, nullptr, kActRelu), s));
+        GemmCall g2 = conv_call(h, h->s16a, T, 1024, h->sem_rb3, 1024, 3, 1, h->sx, true, 1024, h->sr, kActNone);
+        g2.out16 = h->s16b;
+        g2.ld16 = 1024;
+        ENC_RUN(launch_gemm(g2, s));
+        GemmCall g3 = conv_call(h, h->s16b, T, 1024, h->sem_final, 1024, 3, 1, h->sem32, true, 1024, nullptr, kActNone);
+        g3.out16 = h->cat16;  // left half of [semantic | acoustic]
+        g3.ld16 = 2048;
+        ENC_RUN(launch_gemm(g3, s));
+    }
+    // ---- fusion + quantise ----
+    ENC_RUN(launch_gemm(conv_call(h, h->cat16, T, 2048, h->fusion, 2048, 1, 1, h->hid32, true, 2048, nullptr, kActNone), s));
+    if (ids_dev != nullptr) {
+        ENC_RUN(launch_fsq_quantize(h->hid32, 2048, T, h->m("quantizer.project_in.weight"), h->m("quantizer.project_in.bias"),
+                                    2048, pre_bound, ids_dev, id_type, nullptr, s));
+    }
+    if (hidden_dev) B200_CUDA_OK(cudaMemcpyAsync(hidden_dev, h->hid32, static_cast<size_t>(T) * 2048 * 4, cudaMemcpyDeviceToDevice, s));
+    if (acoustic_dev) B200_CUDA_OK(cudaMemcpyAsync(acoustic_dev, h->ac32, static_cast<size_t>(T) * 1024 * 4, cudaMemcpyDeviceToDevice, s));
+    if (semantic_dev) B200_CUDA_OK(cudaMemcpyAsync(semantic_dev, h->sem32, static_cast<size_t>(T) * 1024 * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// Debug / stage parity: fp32 copy of an acoustic-encoder stage of the LAST encode, token-major [rows][C]
+// (pad channels dropped): "conv0" (S rows, 48), "block1".."block5" (EncoderBlock outputs: rows S/2 .. S/320).
+int b200enc_read_stage(B200Enc* h, const char* name, int64_t n_samples, float* host_out, size_t n_elems, void* stream) {
+    B200_CHECK(h && name && host_out, "b200enc_read_stage: null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    B200_CHECK(h->taps_on && n_samples > 0 && n_samples == h->tap_samples,
+               "read_stage: enable b200enc_set_stage_taps and encode %lld samples first", (long long)n_samples);
+    int idx = -1;
+    if (std::strcmp(name, "conv0") == 0) idx = 0;
+    else if (std::strncmp(name, "block", 5) == 0 && name[5] >= '1' && name[5] <= '5' && name[6] == 0) idx = name[5] - '0';
+    B200_CHECK(idx >= 0, "read_stage: unknown stage \"%s\"", name);
+    int64_t rows = n_samples;
+    int c = kGenFeatures;
+    for (int i = 0; i < idx; ++i) {
+        rows /= kStrides[i];
+        c *= 2;
+    }
+    const int P = pad64(c);
+    B200_CHECK(static_cast<size_t>(rows) * c == n_elems, "read_stage %s: expected %lld x %d elements, got %zu", name,
+               (long long)rows, c, n_elems);
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    B200_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    B200_CUDA_OK(cudaMemcpy2D(host_out, static_cast<size_t>(c) * 4, h->tap[idx].p, static_cast<size_t>(P) * 4,
+                              static_cast<size_t>(c) * 4, static_cast<size_t>(rows), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200enc_set_stage_taps(B200Enc* h, int on) {
+    B200_CHECK(h != nullptr, "null handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->taps_on = on != 0;
+    if (!h->taps_on) {
+        for (auto& t : h->tap) t.release();
+        h->tap_samples = 0;
+    }
+    return 0;
+}
+
+int64_t b200enc_launch_count(const B200Enc* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -236,6 +236,7 @@ unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
 #endif
 
 int g_gemm_narrow_tiles = 1;  // A/B: 0 = 256-wide tiles only
+int g_gemm_early_weights = 1; // A/B: weight loads of a launch's first stages before griddepcontrol.wait
 
 namespace {
 
@@ -254,7 +255,9 @@ int fill_params(const GemmCall& c, GemmParams* out) {
     p.n_store = c.n_store;
     p.k_blocks_per_tap = c.Cin / block_k;
     p.taps = c.taps;
-    p.tap_pad = c.tap_pad >= 0 ? c.tap_pad : c.taps / 2;
+    B200_CHECK(c.tap_dil >= 1, "gemm: tap_dil must be >= 1");
+    p.tap_dil = c.tap_dil;
+    p.tap_pad = c.tap_pad >= 0 ? c.tap_pad : (c.taps / 2) * c.tap_dil;
     p.out = c.out;
     p.ldc = c.ldc;
     p.bias = c.bias;
@@ -362,6 +365,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
         cp.tile_end[0] = cp.num_m * cp.num_n[0];
         cp.full[0] = 0;
         cp.counters = nullptr;
+        cp.early_weights = g_gemm_early_weights;
         cp.g[0] = p;
         return launch_2cta<false>(c.precision, p.gn_stats != nullptr, narrow, maps, cp, stream);
     }
@@ -477,6 +481,7 @@ int launch_gemm_chain(const GemmCall* calls, int n, uint32_t* counters, cudaStre
     if (chain_schedule(cp, kb, clusters, &sched)) return 1;
     cp.sched = sched.dev;
     cp.sched_stride = sched.stride;
+    cp.early_weights = g_gemm_early_weights;
     {
         static const char* e = getenv("B200_CHAIN_DBG");  // timing experiments (tools), never set in production
         cp.dbg = e ? atoi(e) : 0;

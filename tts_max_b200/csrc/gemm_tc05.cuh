@@ -36,7 +36,8 @@ struct GemmParams {
     int n_store;           // columns [0, n_store) are written; multiple of 32
     int k_blocks_per_tap;  // Cin / BLOCK_K
     int taps;              // 1 (linear), 3 or 7 (conv)
-    int tap_pad;           // A row = m + tap - tap_pad
+    int tap_pad;           // A row = m + tap * tap_dil - tap_pad
+    int tap_dil;           // dilation (rows between taps)
     void* out;
     int ldc;               // elements
     const float* bias;     // [n_store] or nullptr
@@ -165,7 +166,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const int kc = kb - tap * p.k_blocks_per_tap;
                     uint8_t* sa = smem + stage * SM::kStageBytes;
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K,
-                                m_blk * kGemmBlockM + tap - p.tap_pad);
+                                m_blk * kGemmBlockM + tap * p.tap_dil - p.tap_pad);
                     tma_load_2d(sa + SM::kABytes, &tmap_b, &full_bar[stage], kb * BLOCK_K,
                                 n_blk * BLOCK_N);
                     if (++stage == kStages) {
@@ -253,6 +254,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (p.act == kActSilu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));  // MUFU.EX2 + MUFU.RCP
+                } else if (p.act == kActRelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (row_ok) {
                     if (p.residual != nullptr) {

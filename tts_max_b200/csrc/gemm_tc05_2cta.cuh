@@ -171,6 +171,7 @@ struct ChainParams {
     // others one -- 4 of ~21 tile units of imbalance (measured: the chain was then no faster in the step).
     const int32_t* sched;
     int sched_stride;
+    int early_weights;  // 1: weight loads of the first stages are issued before griddepcontrol.wait (A/B)
     int dbg;  // timing experiments only (tools): 1 no store-completion wait, 2 no epilogue acquire, 4 no producer fence, 8 no publish
     GemmParams g[kChainMax];
 };
@@ -288,7 +289,12 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
     cluster_sync_relaxed();  // peer barriers initialised, TMEM allocated in both CTAs
     tc05_fence_after();
     if (threadIdx.x == 0) B200_TRACE(1);
-    pdl_wait();  // barrier init, TMEM allocation and the cluster sync overlap the predecessor's tail
+    // Barrier init, TMEM allocation and the cluster sync overlap the predecessor's tail (programmatic
+    // dependent launch). griddepcontrol.wait is per thread and only the threads that read what the predecessor
+    // wrote need it: the producer (A operand) and the epilogue warps (residual, row scale). The producer
+    // first puts the WEIGHT halves of its first stages in flight -- weights are written at load time, never by
+    // a kernel of the decode -- so their DRAM latency (~2.4 us from prologue to first operands in the
+    // in-kernel timeline, cold L2) overlaps the predecessor's tail as well.
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -296,6 +302,26 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // weight halves of the first tile's first stages, before waiting for the predecessor (the ring is
+            // empty: no empty-barrier wait; the leader arms each stage's barrier for all of its bytes)
+            int early_b = 0;
+            {
+                const int tile0 = first_tile();
+                if (tile0 >= 0 && cp.early_weights) {
+                    int g, m_blk, n_blk;
+                    decode_tile(tile0, g, m_blk, n_blk);
+                    const int num_kb = cp.g[g].taps * cp.g[g].k_blocks_per_tap;
+                    const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * kHalfN;
+                    early_b = num_kb < kStages ? num_kb : kStages;
+                    for (int kb = 0; kb < early_b; ++kb) {
+                        if (leader) mbar_arrive_expect_tx(&full_bar[kb], kStageTx);
+                        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[kb]), 0);
+                        tma_load_2d_2cta(smem_u32(smem + kb * SM::kStageBytes) + SM::kABytes, &maps.b[g], full_leader,
+                                         kb * BLOCK_K, n0);
+                    }
+                }
+            }
+            pdl_wait();
             for (int it = 0, tile = first_tile(), tile_next; tile >= 0; tile = tile_next) {
                 tile_next = next_tile(++it, tile);
                 int g, m_blk, n_blk;
@@ -308,14 +334,18 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                 const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * kHalfN;
                 bool dep_pending = kChain && g > 0;  // this m-block of the previous GEMM must be stored first
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    // both CTAs' bytes complete on the leader's barrier
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
                     const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
                     const int tap = kb / pg.k_blocks_per_tap;
                     const int kc = kb - tap * pg.k_blocks_per_tap;
                     const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
-                    tma_load_2d_2cta(sa + SM::kABytes, tmap_b, full_leader, kb * BLOCK_K, n0);  // weights never wait
+                    if (early_b > 0) {
+                        --early_b;  // this stage is armed and its weight half is in flight
+                    } else {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        // both CTAs' bytes complete on the leader's barrier
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+                        tma_load_2d_2cta(sa + SM::kABytes, tmap_b, full_leader, kb * BLOCK_K, n0);  // weights never wait
+                    }
                     if constexpr (kChain) {
                         if (dep_pending) {
                             if (!(cp.dbg & 8)) chain_wait(cp.counters + (g - 1) * cp.num_m + m_blk, cp.full[g - 1]);
@@ -323,7 +353,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                             dep_pending = false;
                         }
                     }
-                    tma_load_2d_2cta(sa, tmap_a, full_leader, kc * BLOCK_K, m0 + tap - pg.tap_pad);
+                    tma_load_2d_2cta(sa, tmap_a, full_leader, kc * BLOCK_K, m0 + tap * pg.tap_dil - pg.tap_pad);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -384,6 +414,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
         // row-per-lane 128-bit writes are bank-conflict-free: the 16-byte group j of row r sits
         // at slot j ^ (r & 7) of its 128-byte fp32 row and at slot j ^ ((r >> 1) & 3) of its
         // 64-byte 16-bit row.
+        pdl_wait();  // residual, row scale, GroupNorm maps: written by predecessors
         constexpr int CH = kGemm2ChunkCols;
         constexpr int kChunks = kHalfN / CH;
         const int ew = warp - 4;
@@ -515,6 +546,9 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                 if (p.act == kActSilu) {
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+                } else if (p.act == kActRelu) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (has_res) {
 #pragma unroll

@@ -92,7 +92,7 @@ int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTab
                  int hop, float* wav, cudaStream_t stream);
 
 // ---- gemm_tc05.cu ----
-enum GemmAct : int { kActNone = 0, kActSilu = 1 };
+enum GemmAct : int { kActNone = 0, kActSilu = 1, kActRelu = 2 };
 struct GemmCall {
     int precision;       // operand dtype
     const void* a;       // [a_rows, Cin]
@@ -101,7 +101,8 @@ struct GemmCall {
     const void* w;       // [N, taps*Cin]
     int N;               // logical out features (rows of w)
     int taps;
-    int tap_pad = -1;    // A row = m + tap - tap_pad; -1 -> taps / 2 ("same" conv)
+    int tap_pad = -1;    // A row = m + tap * tap_dil - tap_pad; -1 -> (taps / 2) * tap_dil ("same" conv)
+    int tap_dil = 1;     // dilation of the conv taps, in rows
     void* out;
     int out_fp32;        // 1 -> fp32 output, 0 -> operand dtype
     int ldc;
