@@ -250,6 +250,8 @@ def measure_c3(dec, dev, rank, world, n_utts, precision, steps=1, warmup=1, e2e=
     e2e_s = gather_ms = None
     if e2e:
         gathered = [torch.empty_like(pcm) for _ in range(world)] if (rank == 0 and world > 1) else None
+        if world > 1:   # untimed: NCCL sets its peer connections up on the first use of a collective
+            sharding.gather_packed(pcm, gathered, dst=0)
         barrier()
         t0 = time.perf_counter()
         decode_shard(True)
