@@ -126,6 +126,32 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
                           const int32_t* seqlens_host, int n_utts, float* wav_host,
                           void* stream);
 
+/* ---- cached streaming (BASELINE config 5's shape) -----------------------------------------
+ * The reference has no streaming decoder (tools/serving/inference.py:155-170 decodes once), and chunking
+ * changes what the model computes. Two definitions are offered:
+ *   "window"  (tts_max_b200/codec/streaming.py, round 1): audio(new) = Decoder.forward(cat(context, new))
+ *             trimmed -- every push recomputes the whole [context | new] window (3x the FLOPs of the new audio
+ *             at 100 + 50 tokens); its oracle is the reference forward on that window;
+ *   "cached"  (this API): a push runs the model on [overlap | new] rows only -- `overlap` (~8) previous tokens
+ *             are recomputed so that the convolutions (receptive field 7 rows before the transformer, 4 after)
+ *             and the ISTFT overlap-add (2 frames) have their left halo, GroupNorm normalises over these rows,
+ *             and attention sees the keys / values of the last `left_context` tokens AS THEY WERE COMPUTED
+ *             WHEN THOSE TOKENS WERE NEW (a per-layer key / value ring; the softmax is order-free and the
+ *             head-indexed rotary embedding carries no position). Its oracle is the CPU restatement of exactly
+ *             this algorithm (oracle/streaming_oracle.py); its quality against the one-shot decode is reported
+ *             next to the window method's in tests/test_streaming.py.
+ * b200codec_stream_push: ids_dev = [n_streams][overlap + new_tokens] packed, wav_dev receives
+ * [n_streams][(overlap + new_tokens) * 320] samples (the caller keeps the last new_tokens * 320 of each stream).
+ * `overlap` <= tokens pushed so far. One state per set of lock-step streams; pushes of one state are serial. */
+typedef struct B200Stream B200Stream;
+int b200codec_stream_create(B200Codec* h, int n_streams, int new_tokens, int left_context, B200Stream** out);
+void b200codec_stream_destroy(B200Stream* st);
+int b200codec_stream_reset(B200Stream* st);
+int b200codec_stream_capacity(const B200Stream* st);  /* tokens per key / value ring */
+int64_t b200codec_stream_tokens(const B200Stream* st); /* tokens pushed per stream since the last reset */
+int b200codec_stream_push(B200Codec* h, B200Stream* st, const void* ids_dev, int id_type, int overlap,
+                          float* wav_dev, void* stream);
+
 /* decode_varlen is asynchronous and takes DEVICE ids, so it cannot range-check them before
  * launching: the FSQ kernel flags ids outside [0, 65535] (and masks them to 16 bits).
  * After synchronising the stream, this returns 1 if any decode since the last call saw such

@@ -122,3 +122,57 @@ def test_streaming_quality_vs_one_shot(gpu_decoders):
     print(f"[streaming] SNR vs one-shot decode, 50-token chunks: {snr}")
     assert snr[450] >= snr[100] - 1.0 and snr[100] >= snr[0] - 1.0
     assert snr[450] >= 10.0     # 450 + 50 = the whole utterance from the last chunk on
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_cached_streaming_vs_its_oracle(gpu_decoders, state_dict, prec):
+    """The cached streaming path (key / value rings, [overlap | new] rows per push) against the CPU restatement
+    of exactly that algorithm (oracle/streaming_oracle.py), push by push: through the warm-up, the ring
+    wrap-around (capacity 30 tokens, 9 pushes of 10) and a reset. The first push has no history: it is the plain
+    decode of the chunk."""
+    from oracle import streaming_oracle
+    from tts_max_b200.codec import streaming
+
+    d = gpu_decoders[prec]
+    n_streams, new, ctx_len, overlap, n_push = 3, 10, 20, 8, 9
+    floor = 40.0 if prec == "bf16" else 55.0
+    ids = torch.randint(0, 65536, (n_streams, new * n_push), generator=torch.Generator().manual_seed(31))
+    sd = streaming.CachedStreamingDecoder(d, n_streams, new_tokens=new, left_context=ctx_len, overlap=overlap)
+    assert sd.capacity == 30
+    for round_ in range(2):
+        ref = streaming_oracle.CachedStreamOracle(state_dict, n_streams, new, ctx_len)
+        for k in range(n_push):
+            ov = min(overlap, k * new)
+            out = sd.push(ids[:, k * new:(k + 1) * new])
+            want = ref.push(ids[:, k * new - ov:(k + 1) * new], ov)
+            assert out.shape == (n_streams, new * 320) and out.is_cuda
+            snr = O.snr_db(want, out.cpu())
+            assert torch.isfinite(out).all() and snr >= floor, (round_, k, snr)
+            if k == 0:
+                plain = d(ids[:, :new].cuda())[:, 0, :]
+                assert (out - plain).abs().max().item() <= 1e-5 * max(1e-3, plain.abs().max().item())
+        sd.reset()
+
+
+@pytest.mark.gpu
+def test_cached_streaming_quality_and_cost(gpu_decoders):
+    """Quality of the two streaming definitions against the one-shot decode (random-init weights: the numbers
+    characterise the methods, not a trained codec) and their cost per push."""
+    from tts_max_b200.codec import streaming
+
+    d = gpu_decoders["bf16"]
+    ids = torch.randint(0, 65536, (4, 500), generator=torch.Generator().manual_seed(23))
+    full = d(ids.cuda())[:, 0, :].cpu()
+    snr = {}
+    for name, make in (("window L=100", lambda: streaming.StreamingDecoder(d, 4, new_tokens=50, left_context=100, use_graph=False)),
+                       ("cached L=100 overlap=8", lambda: streaming.CachedStreamingDecoder(d, 4, 50, 100, overlap=8)),
+                       ("cached L=450 overlap=8", lambda: streaming.CachedStreamingDecoder(d, 4, 50, 450, overlap=8)),
+                       ("cached L=100 overlap=24", lambda: streaming.CachedStreamingDecoder(d, 4, 50, 100, overlap=24))):
+        sdec = make()
+        got = torch.cat([sdec.push(ids[:, k:k + 50]) for k in range(0, 500, 50)], dim=1).cpu()
+        assert got.shape == full.shape and torch.isfinite(got).all()
+        snr[name] = round(O.snr_db(full, got), 2)
+    print(f"[streaming] SNR vs one-shot decode, 50-token pushes: {snr}")
+    # the cached method must be in the same quality class as the window method it replaces on the fast path
+    assert snr["cached L=100 overlap=8"] >= snr["window L=100"] - 6.0

@@ -49,6 +49,12 @@ SIGNATURES = {
     "b200codec_decode_varlen": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_decode_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_take_id_error": (c_int, [c_void_p]),
+    "b200codec_stream_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "b200codec_stream_destroy": (None, [c_void_p]),
+    "b200codec_stream_reset": (c_int, [c_void_p]),
+    "b200codec_stream_capacity": (c_int, [c_void_p]),
+    "b200codec_stream_tokens": (c_int64, [c_void_p]),
+    "b200codec_stream_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b200codec_plan_generation": (c_int64, [c_void_p]),
     "b200codec_set_stage_taps": (c_int, [c_void_p, c_int]),
     "b200codec_stage_width": (c_int, [c_void_p, c_char_p]),

@@ -91,10 +91,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// Work item {q_row, n_q, kv_row0, T_kv}: queries are rows [q_row, q_row + n_q) of the Q tensor (n_q <= 128), keys /
+// values rows [kv_row0, kv_row0 + T_kv) of the K/V tensor. One-shot decode: both are the c_attn output
+// (K at column D, V at 2 D) and kv_row0 / T_kv are the utterance; cached streaming (codec.cu, B200Stream): K/V
+// come from a per-layer ring of the last tokens' keys and values (K at column 0, V at D) -- the softmax does
+// not care about the order of the keys, and the head-indexed rotary embedding carries no position.
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
-attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restrict__ out,
-                      const int4* __restrict__ work, int heads) {
+attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                      T* __restrict__ out, const int4* __restrict__ work, int heads, int k_col0, int v_col0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -116,13 +121,14 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     const bool ctrl_warp = warp == 8;         // control warp; warps 0-7 are softmax warps
     const bool ctrl = ctrl_warp && lane == 0;
     const int4 wk = work[blockIdx.x];
-    const int row0 = wk.x, T_utt = wk.y, q0 = wk.z;
+    const int q_row = wk.x, n_q = wk.y, row0 = wk.z, T_utt = wk.w;  // row0 / T_utt: the keys
     const int head = blockIdx.y;
     const int D = heads * kD;
     const int n_kv = (T_utt + kBK - 1) / kBK;
 
     if (ctrl) {
-        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
         mbar_init(bar_q, 1);
         mbar_init(&bar_kv_full[0], 1);
         mbar_init(&bar_kv_full[1], 1);
@@ -154,8 +160,8 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     auto load_kv = [&](int j) {
         const int s = j & 1;
         mbar_arrive_expect_tx(&bar_kv_full[s], 2 * kTileBytes);
-        tma_load_2d(sK + s * kTileBytes, &tmap_qkv, &bar_kv_full[s], D + head * kD, row0 + j * kBK);
-        tma_load_2d(sV + s * kTileBytes, &tmap_qkv, &bar_kv_full[s], 2 * D + head * kD, row0 + j * kBK);
+        tma_load_2d(sK + s * kTileBytes, &tmap_kv, &bar_kv_full[s], k_col0 + head * kD, row0 + j * kBK);
+        tma_load_2d(sV + s * kTileBytes, &tmap_kv, &bar_kv_full[s], v_col0 + head * kD, row0 + j * kBK);
     };
     auto issue_s = [&](int j) {
         const uint64_t a_desc = umma_desc_k_sw128(smem_u32(sQ));
@@ -168,7 +174,7 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     if (ctrl_warp) {
         if (ctrl) {
             mbar_arrive_expect_tx(bar_q, kTileBytes);
-            tma_load_2d(sQ, &tmap_qkv, bar_q, head * kD, row0 + q0);
+            tma_load_2d(sQ, &tmap_q, bar_q, head * kD, q_row);
             load_kv(0);
             if (n_kv > 1) load_kv(1);
             mbar_wait(bar_q, 0);
@@ -307,9 +313,9 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
     float* red_l = red + (n_kv & 1) * 256;  // the parity not used by the last tile's max exchange
     red_l[half * 128 + r] = l_run;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
-    if (q0 + r < T_utt) {
+    if (r < n_q) {
         const float inv = 1.f / (red_l[r] + red_l[128 + r]);
-        T* dst = out + static_cast<size_t>(row0 + q0 + r) * D + head * kD + half * 32;
+        T* dst = out + static_cast<size_t>(q_row + r) * D + head * kD + half * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint4 u;
@@ -332,14 +338,45 @@ attention_tc05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, T* __restric
 
 }  // namespace
 
-int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
-                          cudaStream_t stream) {
-    if (rs.n_attn128_work <= 0) return 0;
+namespace {
+// keys / values of each stream's NEW rows -> its slots of the layer's ring (cached streaming): row
+// utt_row0[u] + overlap + i of the c_attn output, columns [D, 3 D), goes to ring row u * cap + (wpos + i) % cap
+template <typename T>
+__global__ void __launch_bounds__(256)
+kv_scatter_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ utt_row0, int overlap, int n_new, int D,
+                  T* __restrict__ ring, int cap, int wpos) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int u = blockIdx.y, i = blockIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(utt_row0[u] + overlap + i) * 3 * D + D);
+    uint4* dst = reinterpret_cast<uint4*>(ring + (static_cast<size_t>(u) * cap + (wpos + i) % cap) * 2 * D);
+    for (int k = threadIdx.x; k < 2 * D / 8; k += blockDim.x) dst[k] = src[k];
+}
+}  // namespace
+
+int launch_kv_scatter(int prec, const void* qkv, const int32_t* utt_row0, int n_streams, int overlap, int n_new, int D,
+                      void* ring, int cap, int wpos, cudaStream_t stream) {
+    if (n_streams <= 0 || n_new <= 0) return 0;
+    dim3 grid(n_new, n_streams);
+    if (prec == kPrecBf16)
+        B200_CUDA_OK(launch_kernel(kv_scatter_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream,
+                                   static_cast<const __nv_bfloat16*>(qkv), utt_row0, overlap, n_new, D,
+                                   static_cast<__nv_bfloat16*>(ring), cap, wpos));
+    else
+        B200_CUDA_OK(launch_kernel(kv_scatter_kernel<__half>, grid, dim3(256), 0, stream, static_cast<const __half*>(qkv),
+                                   utt_row0, overlap, n_new, D, static_cast<__half*>(ring), cap, wpos));
+    return 0;
+}
+
+int launch_attention_tc05_ex(int prec, const void* q, int q_rows, int q_ld, const void* kv, int kv_rows, int kv_ld,
+                             int k_col0, int v_col0, const int4* work, int n_work, int heads, void* out,
+                             cudaStream_t stream) {
+    if (n_work <= 0) return 0;
     B200_CHECK(prec == kPrecBf16 || prec == kPrecFp16, "attention: unsupported precision %d", prec);
-    alignas(64) CUtensorMap tm;
-    const int D = heads * kD;
-    if (make_tmap_2d(&tm, qkv, prec == kPrecBf16 ? 0 : 1, rs.rows, 3 * D, 3 * D, 128)) return 1;
-    dim3 grid(rs.n_attn128_work, heads);
+    alignas(64) CUtensorMap tq, tkv;
+    if (make_tmap_2d(&tq, q, prec == kPrecBf16 ? 0 : 1, q_rows, q_ld, q_ld, 128)) return 1;
+    if (make_tmap_2d(&tkv, kv, prec == kPrecBf16 ? 0 : 1, kv_rows, kv_ld, kv_ld, 128)) return 1;
+    dim3 grid(n_work, heads);
     static PerDeviceOnce once;
     if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(attention_tc05_kernel<__nv_bfloat16>,
@@ -356,12 +393,19 @@ int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int hea
     }
     if (prec == kPrecBf16)
         B200_CUDA_OK(launch_kernel(attention_tc05_kernel<__nv_bfloat16>, grid, dim3(kThreads), AttnSmem::kTotal, stream,
-                                   tm, static_cast<__nv_bfloat16*>(out), rs.attn128_work, heads));
+                                   tq, tkv, static_cast<__nv_bfloat16*>(out), work, heads, k_col0, v_col0));
     else
-        B200_CUDA_OK(launch_kernel(attention_tc05_kernel<__half>, grid, dim3(kThreads), AttnSmem::kTotal, stream, tm,
-                                   static_cast<__half*>(out), rs.attn128_work, heads));
+        B200_CUDA_OK(launch_kernel(attention_tc05_kernel<__half>, grid, dim3(kThreads), AttnSmem::kTotal, stream, tq, tkv,
+                                   static_cast<__half*>(out), work, heads, k_col0, v_col0));
     B200_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
+                          cudaStream_t stream) {
+    const int D = heads * kD;
+    return launch_attention_tc05_ex(prec, qkv, rs.rows, 3 * D, qkv, rs.rows, 3 * D, D, 2 * D, rs.attn128_work,
+                                    rs.n_attn128_work, heads, out, stream);
 }
 
 }  // namespace b200

@@ -127,6 +127,22 @@ struct StageTimer {
 
 using namespace b200;
 
+// Cached streaming state: per transformer layer, a ring of the keys and values of each
+// stream's last `cap` tokens, as computed when those tokens were new. See b200codec.h for the semantics.
+struct B200Stream {
+    B200Codec* owner = nullptr;
+    int n_streams = 0, new_tokens = 0, left_context = 0, cap = 0;
+    int64_t seen = 0;            // tokens pushed per stream so far
+    void* kv_slab = nullptr;     // [layers][n_streams * cap + 128][2 C] operand dtype
+    size_t layer_stride = 0;     // bytes between layers
+    int4* work_dev = nullptr;    // attention work items of the current push
+    int4* work_host = nullptr;   // pinned
+    int work_cap = 0;
+    // set by push for forward_impl
+    int overlap = 0, wpos = 0, t_kv = 0, n_work = 0;
+    int list_len = -1, list_tkv = -1;  // what the uploaded work list was built for
+};
+
 struct B200Codec {
     B200CodecConfig cfg;
     int C, H, L, V, hop, n_fft, n_bins;
@@ -203,6 +219,8 @@ struct B200Codec {
     // bumped whenever the plan, the workspace or the statistics buffer is rebuilt or reallocated: a
     // CUDA graph captured from a decode bakes those pointers and contents in (b200codec_plan_generation)
     int64_t generation = 0;
+
+    B200Stream* cur_stream = nullptr;  // non-null only inside b200codec_stream_push
 
     int64_t launches = 0;
     bool profiling = false;
@@ -366,8 +384,8 @@ void plan_fill(const PlanLayout& L, const int32_t* seqlens, int gap, void* host)
             w[0] = static_cast<int32_t>(r); w[1] = T; w[2] = q0; w[3] = 0;
         }
         for (int q0 = 0; q0 < T; q0 += 128) {
-            int32_t* w = hp + L.off_attn128 + 4 * ia2++;
-            w[0] = static_cast<int32_t>(r); w[1] = T; w[2] = q0; w[3] = 0;
+            int32_t* w = hp + L.off_attn128 + 4 * ia2++;  // {q_row, n_q, kv_row0, T_kv}
+            w[0] = static_cast<int32_t>(r) + q0; w[1] = T - q0 < 128 ? T - q0 : 128; w[2] = static_cast<int32_t>(r); w[3] = T;
         }
         for (int b0 = 0; b0 < T; b0 += L.istft_hops) {
             int32_t* w = hp + L.off_istft + 4 * ii++;
@@ -922,7 +940,17 @@ int forward_impl(B200Codec* h, const void* ids_dev, int id_type, float* wav_dev,
             Stage t(h, "qkv_gemm", s);
             RUN(launch_gemm(qkv_call(l), s));
         }
-        {
+        if (h->cur_stream != nullptr) {
+            // cached streaming: this layer's keys / values of the new rows join the ring, then every row of the
+            // push attends to the ring (the cached tokens as they were computed when new + the new ones)
+            Stage t(h, "attention", s);
+            B200Stream* st = h->cur_stream;
+            void* ring = static_cast<uint8_t*>(st->kv_slab) + static_cast<size_t>(l) * st->layer_stride;
+            RUN(launch_kv_scatter(prec, h->qkv, rs.utt_row0, st->n_streams, st->overlap, st->new_tokens, C, ring, st->cap,
+                                  st->wpos, s));
+            RUN(launch_attention_tc05_ex(prec, h->qkv, rs.rows, 3 * C, ring, st->n_streams * st->cap, 2 * C, 0, C,
+                                         st->work_dev, st->n_work, h->H, h->y, s));
+        } else {
             Stage t(h, "attention", s);
             RUN(run_attention(prec, h->qkv, rs, h->H, h->y, s));
         }
@@ -1481,11 +1509,23 @@ int b200codec_finalize_weights(B200Codec* h, void* stream) {
     return 0;
 }
 
+static int ensure_stats(B200Codec* h, int n_utts);
+
 static int decode_varlen_locked(B200Codec* h, const void* ids_dev, int id_type,
                                 const int32_t* seqlens_host, int n_utts, float* wav_dev, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (prepare(h, seqlens_host, n_utts, s)) return 1;
     B200_CHECK(ids_dev && wav_dev, "decode: null device buffer");
+    if (ensure_stats(h, n_utts)) return 1;
+    const int rc = forward(h, ids_dev, id_type, wav_dev, s);
+    if (h->profiling) {
+        cudaStreamSynchronize(s);
+        collect_timers(h);
+    }
+    return rc;
+}
+
+static int ensure_stats(B200Codec* h, int n_utts) {
     // 8 GroupNorm layers x [n_utts][32 groups][sum, sumsq] fp64
     // + one float2 [n_utts][32] (mean, rstd) scratch per GroupNorm layer
     // + per transformer block, 4 GEMMs x ceil(rows / 256) m-block counters of the GEMM chains
@@ -1503,12 +1543,7 @@ static int decode_varlen_locked(B200Codec* h, const void* ids_dev, int id_type,
         h->gn_stats_bytes = need * 2;
     }
     h->chain_ctr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(h->gn_stats) + gn_bytes);
-    const int rc = forward(h, ids_dev, id_type, wav_dev, s);
-    if (h->profiling) {
-        cudaStreamSynchronize(s);
-        collect_timers(h);
-    }
-    return rc;
+    return 0;
 }
 
 int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
@@ -1516,6 +1551,101 @@ int b200codec_decode_varlen(B200Codec* h, const void* ids_dev, int id_type,
     B200_CHECK(h != nullptr, "null handle");
     std::lock_guard<std::mutex> lock(h->mu);
     return decode_varlen_locked(h, ids_dev, id_type, seqlens_host, n_utts, wav_dev, stream);
+}
+
+// ---- cached streaming -----------------------------------------------------------------
+int b200codec_stream_create(B200Codec* h, int n_streams, int new_tokens, int left_context, B200Stream** out) {
+    B200_CHECK(h && out, "stream_create: null argument");
+    B200_CHECK(h->finalized, "stream_create called before b200codec_finalize_weights");
+    B200_CHECK(n_streams > 0 && new_tokens > 0 && left_context >= 0 && n_streams <= 65535, "stream_create: bad sizes");
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    B200Stream* st = new B200Stream();
+    st->owner = h;
+    st->n_streams = n_streams;
+    st->new_tokens = new_tokens;
+    st->left_context = left_context;
+    // ring capacity: the context rounded up to whole pushes, plus the push itself (a push never wraps)
+    st->cap = (left_context + new_tokens - 1) / new_tokens * new_tokens + new_tokens;
+    const size_t es = operand_bytes(h->cfg.precision);
+    st->layer_stride = ((static_cast<size_t>(n_streams) * st->cap + 128) * 2 * h->C * es + 1023) & ~static_cast<size_t>(1023);
+    if (cudaMalloc(&st->kv_slab, st->layer_stride * h->L) != cudaSuccess) {
+        set_error("stream_create: cannot allocate %zu bytes of key / value rings", st->layer_stride * h->L);
+        delete st;
+        return 1;
+    }
+    cudaMemset(st->kv_slab, 0, st->layer_stride * h->L);
+    *out = st;
+    return 0;
+}
+
+void b200codec_stream_destroy(B200Stream* st) {
+    if (!st) return;
+    if (st->owner) {
+        cudaSetDevice(st->owner->cfg.device);
+        cudaDeviceSynchronize();
+    }
+    if (st->kv_slab) cudaFree(st->kv_slab);
+    if (st->work_dev) cudaFree(st->work_dev);
+    if (st->work_host) cudaFreeHost(st->work_host);
+    delete st;
+}
+
+int b200codec_stream_reset(B200Stream* st) {
+    B200_CHECK(st != nullptr, "null stream state");
+    st->seen = 0;  // rows beyond the valid count are never attended to: no need to clear the rings
+    st->list_len = st->list_tkv = -1;
+    return 0;
+}
+
+int b200codec_stream_capacity(const B200Stream* st) { return st ? st->cap : 0; }
+int64_t b200codec_stream_tokens(const B200Stream* st) { return st ? st->seen : 0; }
+
+int b200codec_stream_push(B200Codec* h, B200Stream* st, const void* ids_dev, int id_type, int overlap,
+                          float* wav_dev, void* stream) {
+    B200_CHECK(h && st && ids_dev && wav_dev, "stream_push: null argument");
+    B200_CHECK(st->owner == h, "stream_push: the stream state belongs to another decoder handle");
+    B200_CHECK(h->n_up == 0, "stream_push: the cached streaming path is built for the 16 kHz decoder (no upsampler)");
+    B200_CHECK(overlap >= 0 && overlap <= st->seen && overlap <= st->cap - st->new_tokens,
+               "stream_push: overlap %d must be within the tokens pushed so far (%lld) and the ring's context (%d)", overlap,
+               (long long)st->seen, st->cap - st->new_tokens);
+    std::lock_guard<std::mutex> lock(h->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int len = overlap + st->new_tokens;
+    std::vector<int32_t> seqlens(st->n_streams, len);
+    if (prepare(h, seqlens.data(), st->n_streams, s)) return 1;
+    if (ensure_stats(h, st->n_streams)) return 1;
+    // attention work items: every row of the push is a query; keys = the stream's ring
+    const int tiles = (len + 127) / 128;
+    const int n_work = tiles * st->n_streams;
+    if (n_work > st->work_cap) {
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        if (st->work_dev) cudaFree(st->work_dev);
+        if (st->work_host) cudaFreeHost(st->work_host);
+        st->work_dev = nullptr;
+        st->work_host = nullptr;
+        B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&st->work_dev), sizeof(int4) * n_work * 2));
+        B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&st->work_host), sizeof(int4) * n_work * 2));
+        st->work_cap = n_work * 2;
+    }
+    st->overlap = overlap;
+    st->wpos = static_cast<int>(st->seen % st->cap);
+    const int64_t total = st->seen + st->new_tokens;
+    st->t_kv = static_cast<int>(total < st->cap ? total : st->cap);
+    if (st->list_len != len || st->list_tkv != st->t_kv) {  // steady state: the list of the last push still holds
+        B200_CUDA_OK(cudaStreamSynchronize(s));  // the previous upload may still be reading the pinned list
+        for (int u = 0, w = 0; u < st->n_streams; ++u)
+            for (int q0 = 0; q0 < len; q0 += 128, ++w)
+                st->work_host[w] = make_int4(u * (len + kGap) + q0, len - q0 < 128 ? len - q0 : 128, u * st->cap, st->t_kv);
+        B200_CUDA_OK(cudaMemcpyAsync(st->work_dev, st->work_host, sizeof(int4) * n_work, cudaMemcpyHostToDevice, s));
+        st->list_len = len;
+        st->list_tkv = st->t_kv;
+    }
+    st->n_work = n_work;
+    h->cur_stream = st;
+    const int rc = forward(h, ids_dev, id_type, wav_dev, s);
+    h->cur_stream = nullptr;
+    if (rc == 0) st->seen += st->new_tokens;
+    return rc;
 }
 
 int b200codec_take_id_error(B200Codec* h) {

@@ -28,7 +28,7 @@ struct RowSpace {
     const int32_t* utt_tok0 = nullptr;   // [n] packed token offset (== sample offset / hop)
     const int4* attn_work = nullptr;     // [n_attn_work] {row0, T, q0, 0}
     int n_attn_work = 0;
-    const int4* attn128_work = nullptr;  // [n_attn128_work] {row0, T, q0, 0}, 128-query tiles
+    const int4* attn128_work = nullptr;  // [n_attn128_work] {q_row, n_q, kv_row0, T_kv}, 128-query tiles
     int n_attn128_work = 0;
     const int4* istft_work = nullptr;    // [n_istft_work] {utt, b0, 0, 0}
     int n_istft_work = 0;
@@ -80,6 +80,16 @@ int launch_attention(int prec, const void* qkv, const RowSpace& rs, int heads, v
 // ---- attention_tc05.cu (tcgen05 / TMEM version; the default) ----
 int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
                           cudaStream_t stream);
+// general form: queries from `q` ([q_rows][q_ld], head h at column 64 h), keys / values from `kv`
+// ([kv_rows][kv_ld], K of head h at k_col0 + 64 h, V at v_col0 + 64 h); work[i] = {q_row, n_q, kv_row0, T_kv}
+int launch_attention_tc05_ex(int prec, const void* q, int q_rows, int q_ld, const void* kv, int kv_rows, int kv_ld,
+                             int k_col0, int v_col0, const int4* work, int n_work, int heads, void* out,
+                             cudaStream_t stream);
+
+// cached streaming: copy the keys / values of every stream's n_new newest rows (row utt_row0[u] + overlap + i of
+// the c_attn output [rows][3 D]) into ring [n_streams * cap][2 D] at slot (wpos + i) % cap of stream u
+int launch_kv_scatter(int prec, const void* qkv, const int32_t* utt_row0, int n_streams, int overlap, int n_new, int D,
+                      void* ring, int cap, int wpos, cudaStream_t stream);
 
 // ---- istft.cu ----
 struct IstftTables {
