@@ -384,6 +384,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                     mbar_wait(&full_bar[stage], phase);
                     tc05_fence_after();
                     if (kb == 0 && trace_tile < 4) B200_TRACE(2 + 2 * trace_tile);  // first operands landed
+                    if (kChain && kb == 0 && trace_tile < 24) B200_TRACE(32 + 4 * trace_tile);  // tools/chain_trace.cu
                     const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
                     const uint64_t a_desc = umma_desc_k_sw128(sa);
                     const uint64_t b_desc = umma_desc_k_sw128(sa + SM::kABytes);
@@ -399,6 +400,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                 }
                 umma_commit_2cta(&tmem_full[acc]);  // accumulators of both CTAs complete
                 if (trace_tile < 4) B200_TRACE(3 + 2 * trace_tile);  // last MMA of the tile issued
+                if (kChain && trace_tile < 24) B200_TRACE(32 + 4 * trace_tile + 1);
                 ++trace_tile;
                 if (++acc == 2) {
                     acc = 0;
@@ -492,7 +494,8 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                 float tot = 0.f;
 #pragma unroll
                 for (int i = 0; i < kGemmSsSlots / 4; ++i) {
-                    const float4 s4 = sp[i];
+                    // chains: an SM may have read this row's partials for an earlier GEMM of the same launch
+                    const float4 s4 = kChain ? __ldcg(sp + i) : sp[i];
                     tot += (s4.x + s4.y) + (s4.z + s4.w);
                 }
                 rscale = rsqrtf(tot * p.ss_inv_dim + p.ss_eps) * p.ss_in_scale;
@@ -500,6 +503,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
             mbar_wait(&tmem_full[acc], acc_phase);
             tc05_fence_after();
             if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(10 + 2 * trace_tile);  // accumulator ready
+            if (kChain && warp == 4 && lane == 0 && trace_tile < 24) B200_TRACE(32 + 4 * trace_tile + 2);
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                     static_cast<uint32_t>(acc * BLOCK_N + hh * kHalfN);
             uint32_t r_next[CH];
@@ -508,7 +512,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
             for (int c = 0; c < kChunks; ++c) {
                 const int n0 = ncol0 + c * CH;
 #ifdef B200_GEMM_TRACE
-                const bool tr = warp == 4 && lane == 0 && trace_tile < 2;
+                const bool tr = !kChain && warp == 4 && lane == 0 && trace_tile < 2;
                 const int tslot = 32 + trace_tile * 48 + c * 6;
                 if (tr) B200_TRACE(tslot + 0);
 #endif
@@ -650,6 +654,7 @@ gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_const
                 }
             }
             if (warp == 4 && lane == 0 && trace_tile < 4) B200_TRACE(11 + 2 * trace_tile);  // tile drained
+            if (kChain && warp == 4 && lane == 0 && trace_tile < 24) B200_TRACE(32 + 4 * trace_tile + 3);
             ++trace_tile;
             if (++acc == 2) {
                 acc = 0;
