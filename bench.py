@@ -32,6 +32,7 @@ HOP = 320
 
 WORKLOADS = {
     # name: (description, utterances, tokens per utterance)
+    "b1": ("1 clip x 5 s (the shape of AudioDecoder.decode, decoding.py:84-89; not a BASELINE config)", 1, 250),
     "c1": ("4 clips x 5 s (BASELINE config 1, the reference's CPU case)", 4, 250),
     "c2": ("16 clips x 10 s (BASELINE config 2)", 16, 500),
     "c4": ("4 clips x 60 s long-form (BASELINE config 4)", 4, 3000),

@@ -334,3 +334,22 @@ def test_config3_bucket_vs_oracle(gpu_decoders, state_dict):
         for k in (0, len(bucket) // 2, len(bucket) - 1):
             ref = O.decoder_forward(state_dict, utts[bucket[k]].view(1, -1))[0, 0]
             check_wave(ref, wav[offs[k] * 320:offs[k + 1] * 320], prec, f"config3 pack member {k} (T = {seqlens[k]})")
+
+
+def test_output_guard_bands(gpu_decoders):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted by hand: the PCM buffer is
+    a slice of a larger tensor filled with a sentinel, for ragged shapes around every tile size (ISTFT tiles of
+    12 / 28 hops, 128-row attention tiles, 256-row GEMM blocks); the guard bands must survive and every sample
+    inside must have been written."""
+    d = gpu_decoders["bf16"]
+    g = torch.Generator().manual_seed(11)
+    pad = 4096
+    for lens in ([1], [11, 12, 13], [27, 28, 29, 1], [127, 128, 129], [255, 256, 257], [500] * 5 + [3], [1200, 37]):
+        n = 320 * sum(lens)
+        big = torch.full((n + 2 * pad,), 7777.0, device="cuda")
+        ids = torch.randint(0, 65536, (sum(lens),), generator=g).cuda()
+        out = d.decode_packed_device(ids, lens, out=big[pad:pad + n])
+        torch.cuda.synchronize()
+        assert out.data_ptr() == big[pad:].data_ptr()
+        assert bool((big[:pad] == 7777.0).all()) and bool((big[pad + n:] == 7777.0).all()), lens
+        assert torch.isfinite(out).all() and not bool((out == 7777.0).any()), lens
