@@ -49,7 +49,8 @@ int main(int argc, char** argv) {
     fill_kernel<<<1024, 256>>>(qkv, static_cast<size_t>(rows) * 3 * D, 7);
     std::vector<int4> work;
     for (int u = 0; u < n_utts; ++u)
-        for (int q0 = 0; q0 < T; q0 += 128) work.push_back(make_int4(u * pitch, T, q0, 0));
+        for (int q0 = 0; q0 < T; q0 += 128)  // {q_row, n_q, kv_row0, T_kv}
+            work.push_back(make_int4(u * pitch + q0, T - q0 < 128 ? T - q0 : 128, u * pitch, T));
     int4* work_dev;
     cudaMalloc(&work_dev, work.size() * sizeof(int4));
     cudaMemcpy(work_dev, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice);
