@@ -72,20 +72,30 @@ enc_conv0_kernel(const float* __restrict__ wav, int S, const float* __restrict__
                  const float* __restrict__ bias, int C, int P, float* __restrict__ out /*[S][P]*/) {
     pdl_launch_dependents();
     pdl_wait();
-    const int c = threadIdx.x % P;  // blockDim.x is a multiple of P
-    const int rows_per_block = blockDim.x / P;
-    const int t = blockIdx.x * rows_per_block + threadIdx.x / P;
+    // a thread owns 4 channels of one sample (128-bit stores); P / 4 threads per sample
+    const int tpr = P >> 2;
+    const int c0 = (threadIdx.x % tpr) * 4;
+    const int t = blockIdx.x * (blockDim.x / tpr) + threadIdx.x / tpr;
     if (t >= S) return;
-    float acc = 0.f;
-    if (c < C) {
-        acc = bias[c];
+    float xin[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const int i = t + k - 3;
-            if (i >= 0 && i < S) acc = fmaf(w[c * 7 + k], __ldg(wav + i), acc);
-        }
+    for (int k = 0; k < 7; ++k) {
+        const int i = t + k - 3;
+        xin[k] = (i >= 0 && i < S) ? __ldg(wav + i) : 0.f;
     }
-    out[static_cast<size_t>(t) * P + c] = acc;
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        float a = 0.f;
+        if (c < C) {
+            a = bias[c];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) a = fmaf(w[c * 7 + k], xin[k], a);
+        }
+        acc[j] = a;
+    }
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(t) * P + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // Activation1d(SnakeBeta) fused (activations.py:90-110, filters.py:87-135 with ratio 2, 12-tap kaiser-sinc
@@ -687,7 +697,7 @@ int b200enc_encode(B200Enc* h, const float* wav_dev, int64_t n_samples, const fl
     const bool bf = h->precision == kPrecBf16;
 
     // ---- acoustic encoder ----
-    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 3) / 4), dim3(256), 0, s, wav_dev, S, (const float*)h->conv0_w,
+    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 15) / 16), dim3(256), 0, s, wav_dev, S, (const float*)h->conv0_w,
                                (const float*)h->conv0_b, kGenFeatures, 64, h->x[0]));
     h->launches++;
     auto take_tap = [&](int idx, int64_t r, int Pc) -> int {

@@ -206,6 +206,10 @@ enum GemmKind { kGemm1CtaN128 = 0, kGemm1CtaN256 = 1, kGemm2Cta = 2 };
 static GemmKind gemm_kind(const GemmCall& c) {
     const bool n256 = c.n_store >= 256 && (c.n_store % 256 == 0);
     if (n256) return kGemm2Cta;
+    // N a multiple of 64 but not of 256 (the encoder's 64 ... 384-channel convs): the CTA-pair kernel's 256 x 64
+    // tiles. Its TMA-store epilogue drains a tile several times faster than the 1-CTA kernel's row-per-lane
+    // stores, and these GEMMs (K = 64 ... 1344, 10^5 rows) are epilogue-bound
+    if (c.n_store >= 64 && c.n_store % 64 == 0) return kGemm2Cta;
     if (n256 && c.n_store >= 1024) return kGemm1CtaN256;
     return kGemm1CtaN128;
 }
@@ -354,7 +358,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     if (fill_params(c, &p)) return 1;
     if (c.a_rows <= 0) return 0;
     if (gemm_kind(c) == kGemm2Cta) {
-        const bool narrow = c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store);
+        const bool narrow = c.n_store % 256 != 0 || (c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store));
         const int block_n = narrow ? 64 : 256;
         alignas(64) ChainMaps maps;
         ChainParams cp{};
