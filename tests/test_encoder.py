@@ -171,3 +171,29 @@ def test_gpu_encoder_batch_equals_single_and_round_trip(gpu_encoders, gpu_decode
     calls = []
     ids2 = enc.encode(long_wav, lambda audio_pad: (calls.append(tuple(audio_pad.shape)), torch.zeros(1, 200, 1024))[1])
     assert calls == [(1, 64320)] and ids2.shape == (200,)
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_errors(gpu_encoders):
+    import ctypes
+
+    from tts_max_b200 import _lib
+
+    enc = gpu_encoders["bf16"]
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 1, 321, device="cuda"), torch.zeros(1, 1, 1024, device="cuda"))
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 1, 640, device="cuda"), torch.zeros(1, 3, 1024, device="cuda"))
+    lib = _lib.load()
+    x = torch.zeros(640, device="cuda")
+    rc = lib.b200enc_encode(enc._ensure_handle(), ctypes.c_void_p(x.data_ptr()), 333, ctypes.c_void_p(x.data_ptr()), None, 0, 0,
+                            None, None, None, None)
+    assert rc != 0 and b"multiple of 320" in lib.b200codec_last_error()
+    with pytest.raises(_lib.B200CodecError):
+        enc.read_stage("conv0", 640)          # taps are off
+    # ragged lengths back to back (workspace regrowth) stay finite and deterministic
+    g = torch.Generator().manual_seed(9)
+    for T in (1, 3, 200, 7, 64):
+        wav, w2v = 0.3 * torch.randn(1, 1, 320 * T, generator=g), torch.randn(1, T, 1024, generator=g)
+        a = enc(wav.cuda(), w2v.cuda())
+        assert a.shape == (1, 1, T) and torch.equal(a, enc(wav.cuda(), w2v.cuda()))

@@ -176,3 +176,36 @@ def test_cached_streaming_quality_and_cost(gpu_decoders):
     print(f"[streaming] SNR vs one-shot decode, 50-token pushes: {snr}")
     # the cached method must be in the same quality class as the window method it replaces on the fast path
     assert snr["cached L=100 overlap=8"] >= snr["window L=100"] - 6.0
+
+
+@pytest.mark.gpu
+def test_cached_streaming_errors_and_isolation(gpu_decoders):
+    """Error paths of the stream ABI are Python exceptions, a state belongs to its decoder, and ordinary decodes
+    between pushes do not disturb the rings (they live outside the decode workspace)."""
+    import ctypes
+
+    from tts_max_b200 import _lib
+    from tts_max_b200.codec import streaming
+
+    d, other = gpu_decoders["bf16"], gpu_decoders["fp16"]
+    with pytest.raises(ValueError):
+        streaming.CachedStreamingDecoder(d, 0)
+    sd = streaming.CachedStreamingDecoder(d, 2, new_tokens=10, left_context=20, overlap=8)
+    ids = torch.randint(0, 65536, (2, 60), generator=torch.Generator().manual_seed(3)).cuda()
+    with pytest.raises(ValueError):
+        sd.push(ids[:, :11])
+    lib = _lib.load()
+    wav = torch.empty(2, 18 * 320, device="cuda")
+    # overlap larger than the tokens pushed so far; a state used with another decoder's handle
+    rc = lib.b200codec_stream_push(d._ensure_handle(), sd._state, ctypes.c_void_p(ids.data_ptr()), _lib.IDS_I64, 8,
+                                   ctypes.c_void_p(wav.data_ptr()), None)
+    assert rc != 0 and b"overlap" in lib.b200codec_last_error()
+    rc = lib.b200codec_stream_push(other._ensure_handle(), sd._state, ctypes.c_void_p(ids.data_ptr()), _lib.IDS_I64, 0,
+                                   ctypes.c_void_p(wav.data_ptr()), None)
+    assert rc != 0 and b"another decoder" in lib.b200codec_last_error()
+    ref = streaming.CachedStreamingDecoder(d, 2, new_tokens=10, left_context=20, overlap=8)
+    for k in range(6):
+        a = sd.push(ids[:, 10 * k:10 * k + 10])
+        d(torch.randint(0, 65536, (3, 77 + k), generator=torch.Generator().manual_seed(k)).cuda())   # foreign decode
+        b = ref.push(ids[:, 10 * k:10 * k + 10])
+        assert (a - b).abs().max().item() <= 1e-5 * max(1e-3, b.abs().max().item()), k
