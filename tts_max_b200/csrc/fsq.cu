@@ -459,4 +459,55 @@ int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// LLM token ids -> FSQ code ids. The reference detokenises a completion to a string, tokenises
+// it again and parses "<|s_N|>" (rewards.py:70-73, inferencing.py:53-63). The speech tokens are added to the
+// tokenizer in SORTED (lexicographic) order (tokenization.py:36-49), so vocabulary id -> N is a permutation, not an
+// offset: `table[v]` holds N for a speech token and -1 for anything else. One CTA per sequence keeps the speech
+// tokens in order (ballot + prefix sums) and writes them packed at the sequence's own offset.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+map_speech_tokens_kernel(const int32_t* __restrict__ table, int vocab, const long long* __restrict__ tok,
+                         const int32_t* __restrict__ seq_off, int32_t* __restrict__ codes, int32_t* __restrict__ out_len) {
+    __shared__ int warp_cnt[8];
+    __shared__ int base;
+    const int s = blockIdx.x;
+    const int lo = seq_off[s], hi = seq_off[s + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int i0 = lo; i0 < hi; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        int code = -1;
+        if (i < hi) {
+            const long long v = tok[i];
+            if (v >= 0 && v < vocab) code = table[v];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, code >= 0);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+        if (code >= 0) codes[lo + before + __popc(m & ((1u << lane) - 1u))] = code;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_len[s] = base;
+}
+}  // namespace
+
+int launch_map_speech_tokens(const int32_t* table, int vocab, const long long* tok, const int32_t* seq_off, int n_seq,
+                             int32_t* codes, int32_t* out_len, cudaStream_t stream) {
+    if (n_seq <= 0) return 0;
+    map_speech_tokens_kernel<<<n_seq, 256, 0, stream>>>(table, vocab, tok, seq_off, codes, out_len);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace b200

@@ -59,6 +59,11 @@ int launch_fsq_im2col(const void* ids, int id_type, const int32_t* row_tok, int 
 int launch_fsq_quantize(const float* x, int ld, int n_tokens, const float* w_in, const float* b_in,
                         int dim, int pre_bound, void* ids, int id_type, float* z_out, cudaStream_t stream);
 
+// LLM vocabulary ids -> FSQ code ids: table[v] = N for "<|s_N|>", -1 otherwise; sequence s is tok[seq_off[s] ..
+// seq_off[s + 1]); its speech tokens are written, in order, to codes[seq_off[s] ..] and counted in out_len[s]
+int launch_map_speech_tokens(const int32_t* table, int vocab, const long long* tok, const int32_t* seq_off, int n_seq,
+                             int32_t* codes, int32_t* out_len, cudaStream_t stream);
+
 // ---- norms.cu ----
 // w == nullptr: no elementwise weight (it is folded into the consumer GEMM's weight columns)
 int launch_rmsnorm(int prec, const float* x, const float* w, int rows, int dim, float eps,
