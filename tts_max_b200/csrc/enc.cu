@@ -100,7 +100,8 @@ enc_conv0_kernel(const float* __restrict__ wav, int S, const float* __restrict__
 
 // Activation1d(SnakeBeta) fused (activations.py:90-110, filters.py:87-135 with ratio 2, 12-tap kaiser-sinc
 // filters, replicate padding):
-//   u[2t]   = 2 sum_j fu[2j+1] x[t+2-j]       u[2t+1] = 2 sum_j fu[2j] x[t+3-j]      (j = 0..5, rows clamped)
+//   u[2t]   = 2 sum_j fu[2j+1] x[t+2-j]       u[2t+1] = 2 sum_j fu[2j] x[t+3-j]      (j = 0..5, rows clamped;
+//                                                                                    the 2 is folded into f.up)
 //   s[n]    = u[n] + sin^2(u[n] e^alpha) / (e^beta + 1e-9)                           (n in [0, 2T))
 //   y[t]    = sum_k fd[k] s[clamp(2t + k - 5, 0, 2T - 1)]                            (k = 0..11)
 // A thread owns one channel and kSnakeRows consecutive rows: the 2 * rows + 10 snake values it needs live in
@@ -133,12 +134,19 @@ snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restri
         const float sn = __sinf(r);
         return fmaf(sn * sn, ib, u);
     };
-    // rows t0 - 6 .. t0 + K + 5 (clamped)
+    // rows t0 - 6 .. t0 + K + 5 (clamped at the two ends of the utterance; interior threads -- all but the first
+    // and the last chunk -- step one pointer instead of clamping and re-deriving a 64-bit address per row)
     float xr[K + 12];
+    if (t0 >= 6 && t0 + K + 5 < T) {
+        const float* px = x + static_cast<size_t>(t0 - 6) * P + c;
 #pragma unroll
-    for (int r = 0; r < K + 12; ++r) {
-        const int t = min(max(t0 - 6 + r, 0), T - 1);
-        xr[r] = __ldg(x + static_cast<size_t>(t) * P + c);
+        for (int r = 0; r < K + 12; ++r, px += P) xr[r] = __ldg(px);
+    } else {
+#pragma unroll
+        for (int r = 0; r < K + 12; ++r) {
+            const int t = min(max(t0 - 6 + r, 0), T - 1);
+            xr[r] = __ldg(x + static_cast<size_t>(t) * P + c);
+        }
     }
     // s[n] for n = 2 t0 - 5 + q, q = 0 .. 2K + 9; row t = t0 - 3 + (q + 1) / 2 for odd n (q even), t0 - 2 + q / 2 ...
     float sv[2 * K + 10];
@@ -156,14 +164,14 @@ snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restri
 #pragma unroll
             for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j], xr[tr + 3 - j], u);
         }
-        sv[q] = snake(2.f * u);
+        sv[q] = snake(u);
     }
     // replicate padding of the UP-SAMPLED signal at the two ends of the utterance (warp-uniform branches)
     if (2 * t0 - 5 < 0) {
         float u = 0.f;  // s[0]: n = 0 = 2 * 0, rows 2, 1, 0, -1, -2, -3 clamped
 #pragma unroll
         for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j + 1], __ldg(x + static_cast<size_t>(min(max(2 - j, 0), T - 1)) * P + c), u);
-        const float s0 = snake(2.f * u);
+        const float s0 = snake(u);
 #pragma unroll
         for (int q = 0; q < 5; ++q)
             if (2 * t0 - 5 + q < 0) sv[q] = s0;
@@ -172,7 +180,7 @@ snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restri
         float u = 0.f;  // s[2T - 1]: n odd = 2 (T - 1) + 1, rows T+2, T+1, T, T-1, T-2, T-3 clamped
 #pragma unroll
         for (int j = 0; j < 6; ++j) u = fmaf(f.up[2 * j], __ldg(x + static_cast<size_t>(min(max(T - 1 + 3 - j, 0), T - 1)) * P + c), u);
-        const float sl = snake(2.f * u);
+        const float sl = snake(u);
 #pragma unroll
         for (int q = 0; q < 2 * K + 10; ++q)
             if (2 * t0 - 5 + q > 2 * T - 1) sv[q] = sl;
@@ -593,7 +601,7 @@ int b200enc_finalize_weights(B200Enc* h, void* stream) {
         B200_CUDA_OK(cudaMemcpy(fu, h->m(p + "upsample.filter"), sizeof(fu), cudaMemcpyDeviceToHost));
         B200_CUDA_OK(cudaMemcpy(fd, h->m(p + "downsample.lowpass.filter"), sizeof(fd), cudaMemcpyDeviceToHost));
         for (int i = 0; i < 12; ++i) {
-            w->f.up[i] = fu[i];
+            w->f.up[i] = 2.f * fu[i];  // UpSample1d multiplies its output by the ratio (filters.py:111)
             w->f.down[i] = fd[i];
         }
         return 0;
