@@ -62,6 +62,7 @@ class StreamingDecoder:
         self._graph: torch.cuda.CUDAGraph | None = None
         self._graph_wav: torch.Tensor | None = None
         self._graph_generation = -1  # Decoder.plan_generation() right after capture
+        self._stale_captures = 0     # consecutive captures that were invalidated before their first replay
 
     # ------------------------------------------------------------------------------------------
     def reset(self) -> None:
@@ -108,9 +109,16 @@ class StreamingDecoder:
         # reset(), or an unrelated decode between pushes) rewrites or reallocates them, so the graph is
         # replayed only while the handle's plan generation is the one seen right after capture.
         if self._graph is not None and self._dec.plan_generation() == self._graph_generation:
+            self._stale_captures = 0
             self._graph.replay()
             return self._graph_wav.view(self.n_streams, -1)
+        if self._graph is not None:
+            self._stale_captures += 1
         self._graph = None
+        if self._stale_captures >= 3:
+            # something decodes other shapes on this decoder between every two pushes: capturing again each time
+            # would cost more than the replay saves
+            return self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
         # eager decode of this push: the result, and the plan / workspace / tensor maps of this shape
         wav = self._dec.decode_packed_device(self._window.view(-1), seqlens).view(self.n_streams, -1)
         # capture for the NEXT push (the capture itself executes nothing)
