@@ -75,6 +75,8 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.rows: list[list[str]] = []
+        self._first = threading.Event()
+        self._lo, self._hi = 0, None
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
@@ -83,12 +85,25 @@ class ClockSampler:
             proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                      "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
         except Exception:
+            self._first.set()
             return
         self._proc = proc
         for line in proc.stdout:
             if self._stop.is_set():
                 break
             self.rows.append([c.strip() for c in line.split(",")])
+            self._first.set()
+        self._first.set()
+
+    def mark_start(self, timeout: float = 10.0):
+        """Blocks until nvidia-smi has delivered its first row (its start-up can take longer than a short
+        timed region), then marks the beginning of the timed region."""
+        self._first.wait(timeout)
+        self._lo = len(self.rows)
+
+    def mark_end(self):
+        time.sleep(0.03)  # one more sampling period, so that a short region still holds its last sample
+        self._hi = len(self.rows)
 
     def __enter__(self):
         self._thread.start()
@@ -104,7 +119,8 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[max(self._lo - 1, 0):self._hi]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -238,12 +254,13 @@ def measure_c3(dec, dev, rank, world, n_utts, precision, steps=1, warmup=1, e2e=
     launches0 = dec.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index or 0) as clocks:
-        time.sleep(0.15)
+        clocks.mark_start()
         e0.record()
         for _ in range(steps):
             decode_shard(False)
         e1.record()
         barrier()
+        clocks.mark_end()
     my_ms = e0.elapsed_time(e1) / steps
     launches = (dec.launch_count() - launches0) // steps
 
@@ -420,7 +437,7 @@ def run_ours(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
-        time.sleep(0.15)  # let the sampler start
+        clocks.mark_start()  # waits for the sampler's first row
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()  # L2 flush between timed steps (outside the per-step event bracket)
@@ -429,6 +446,7 @@ def run_ours(args):
             ends[i].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        clocks.mark_end()
     launches = dec.launch_count() - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     dev_ms_total = sum(step_ms)
@@ -538,12 +556,13 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as sclk:
-            time.sleep(0.15)
+            sclk.mark_start()
             s0.record()
             for _ in range(n_loop):
                 dec.decode_packed_device(ids_dev, seqlens)
             s1.record()
             torch.cuda.synchronize(dev)
+            sclk.mark_end()
         sus_ms = s0.elapsed_time(s1) / n_loop
         sc = sclk.summary()
         sustained = {
