@@ -178,10 +178,6 @@ int b200codec_stage_width(B200Codec* h, const char* name);
 int64_t b200codec_stage_rows(B200Codec* h, const char* name);
 int b200codec_read_stage(B200Codec* h, const char* name, float* host_out, size_t n_elems, void* stream);
 
-/* Process-wide choice of the attention kernel: 0 = tcgen05 / TMEM (default), 1 = the mma.sync
- * flash kernel it replaced (kept for A/B measurements and as a second opinion in the tests). */
-int b200codec_set_attention_impl(int impl);
-
 /* Front end (ids -> embed output). project_out, fc_post_a and the backbone's embed conv (k = 7) are
  * linear maps back to back, so the conv output is a linear function of the 7 neighbouring codes whose
  * coefficients are folded in fp64 at load time. mode 1 (default): im2col of the codes (exact in 16 bits)

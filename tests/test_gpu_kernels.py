@@ -200,17 +200,9 @@ def test_groupnorm_swish_varlen(prec):
 # ----------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------
-@pytest.fixture(params=[0, 1], ids=["tcgen05", "mma_sync"])
-def attn_impl(request):
-    """Both attention kernels (the TMEM one is the default; the mma.sync one is the second opinion)."""
-    _lib.check(_lib.load().b200codec_set_attention_impl(request.param))
-    yield request.param
-    _lib.check(_lib.load().b200codec_set_attention_impl(0))
-
-
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("seqlens", [[64], [1], [37, 250], [65, 128, 500, 3], [129, 127, 256, 257]])
-def test_attention_varlen(prec, seqlens, attn_impl):
+def test_attention_varlen(prec, seqlens):
     code, dt = PREC[prec]
     g = torch.Generator(device="cuda").manual_seed(sum(seqlens))
     rows = sum(seqlens)
@@ -231,7 +223,7 @@ def test_attention_varlen(prec, seqlens, attn_impl):
         off += T
 
 
-def test_attention_long_form(attn_impl):
+def test_attention_long_form():
     code, dt = PREC["bf16"]
     T = 3000
     g = torch.Generator(device="cuda").manual_seed(9)

@@ -65,8 +65,8 @@ for (mangled, body), dem in zip(funcs.items(), names):
 git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
 lines = [f"# {args.tag}: SASS mnemonic counts per kernel of tts_max_b200/lib/libb200codec.so (sm_100a), sources at {git}", "",
          "`python tools/sass_summary.py --tag " + args.tag + "` (cuobjdump -sass | c++filt). tcgen05.mma = UTCHMMA, tcgen05.commit = UTCBAR, "
-         "TMA load / store = UTMALDG / UTMASTG, tcgen05.ld / st = LDTM / STTM; HMMA only in the mma.sync attention kernel kept as a "
-         "second opinion. Full listings: " + ", ".join(f"`profiles/sass/{args.tag}_{v}.sass`" for v in FULL.values()) + ".", "",
+         "TMA load / store = UTMALDG / UTMASTG, tcgen05.ld / st = LDTM / STTM; an HMMA (mma.sync) count other than 0 would be a "
+         "legacy tensor-core path. Full listings: " + ", ".join(f"`profiles/sass/{args.tag}_{v}.sass`" for v in FULL.values()) + ".", "",
          "| kernel | instr | " + " | ".join(COLS) + " |", "|---|---:|" + "---:|" * len(COLS)]
 for name, n, cnt in sorted(rows, key=lambda r: r[0]):
     lines.append(f"| `{name}` | {n} | " + " | ".join(str(cnt[c]) for c in COLS) + " |")

@@ -60,7 +60,6 @@ SIGNATURES = {
     "b200codec_stage_width": (c_int, [c_void_p, c_char_p]),
     "b200codec_stage_rows": (c_int64, [c_void_p, c_char_p]),
     "b200codec_read_stage": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
-    "b200codec_set_attention_impl": (c_int, [c_int]),
     "b200codec_set_zero_copy_output": (c_int, [c_int]),
     "b200codec_set_gemm_narrow_tiles": (c_int, [c_int]),
     "b200codec_set_istft_tile": (c_int, [c_int]),

@@ -49,12 +49,9 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-int g_attention_impl = 0;  // 0 = tcgen05 (default), 1 = legacy mma.sync kernel (A/B testing)
-
 int run_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
                   cudaStream_t s) {
-    return g_attention_impl == 1 ? launch_attention(prec, qkv, rs, heads, out, s)
-                                 : launch_attention_tc05(prec, qkv, rs, heads, out, s);
+    return launch_attention_tc05(prec, qkv, rs, heads, out, s);
 }
 
 constexpr int kGap = 3;          // zero rows between utterances (conv7 halo)
@@ -1767,12 +1764,6 @@ int b200codec_read_stage(B200Codec* h, const char* name, float* host_out, size_t
         }
         r += static_cast<size_t>(kGap) * factor;
     }
-    return 0;
-}
-
-int b200codec_set_attention_impl(int impl) {
-    B200_CHECK(impl == 0 || impl == 1, "attention impl must be 0 (tcgen05) or 1 (mma.sync)");
-    g_attention_impl = impl;
     return 0;
 }
 

@@ -79,10 +79,7 @@ int launch_groupnorm_apply_swish(int prec, const float* x, const RowSpace& rs, i
                                  const double* stats, const float* gamma, const float* beta,
                                  float eps, void* out, cudaStream_t stream);
 
-// ---- attention.cu ----
-int launch_attention(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
-                     cudaStream_t stream);
-// ---- attention_tc05.cu (tcgen05 / TMEM version; the default) ----
+// ---- attention_tc05.cu (tcgen05 / TMEM) ----
 int launch_attention_tc05(int prec, const void* qkv, const RowSpace& rs, int heads, void* out,
                           cudaStream_t stream);
 // general form: queries from `q` ([q_rows][q_ld], head h at column 64 h), keys / values from `kv`
