@@ -213,6 +213,22 @@ def test_full_size_properties(gpu_decoders, shape):
     assert wav.abs().max().item() < 1e3
 
 
+def test_large_batch_index_math(gpu_decoders):
+    """560 x 1000 tokens in ONE call: 561 677 padded rows, so rows x 4096 (the fc1 operand) passes 2^31
+    elements and rows x 1024 x 4 passes 2^31 bytes -- any 32-bit row offset in a kernel shows up in the
+    last utterances. Property: first / middle / last row of the batch == its single decode."""
+    d = gpu_decoders["bf16"]
+    B, T = 560, 1000
+    ids = torch.randint(0, 65536, (B, T), generator=torch.Generator().manual_seed(560)).cuda()
+    wav = d(ids)
+    assert wav.shape == (B, 1, 320 * T) and torch.isfinite(wav).all()
+    for b in (0, B // 2, B - 1):
+        single = d(ids[b:b + 1])
+        assert (wav[b] - single[0]).abs().max().item() <= 1e-5 * max(1e-3, single.abs().max().item()), b
+    del wav
+    torch.cuda.empty_cache()
+
+
 def test_config2_vs_oracle_subsample(gpu_decoders, state_dict):
     """BASELINE config 2 (16 x 10 s, bf16): two of the sixteen clips checked against the oracle."""
     ids = torch.randint(0, 65536, (16, 500), generator=torch.Generator().manual_seed(1234))
