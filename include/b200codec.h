@@ -188,8 +188,10 @@ int b200codec_set_frontend_fold(int mode);
 
 /* GEMM tile width (default on): when M is small (B = 1 serving, BASELINE config 1) the 256-wide tiling
  * would give only N / 256 of the 74 CTA pairs a tile; 256 x 64 tiles spread the same work over four
- * times as many. Every output element sees the same K order, so results are bit-identical. A/B switch. */
-int b200codec_set_gemm_narrow_tiles(int on);
+ * times as many. Every output element sees the same K order, so results are bit-identical. A/B switch:
+ * 0 = 256-wide tiles only, 1 = default (also: 128- / 192-wide tiles for the encoder's N % 256 != 0 convs),
+ * 2 = 64-wide tiles for every N % 256 != 0. */
+int b200codec_set_gemm_narrow_tiles(int mode);
 
 /* Default on: a GEMM launch issues the WEIGHT halves of its first pipeline stages before
  * griddepcontrol.wait (weights are never written by a kernel of the decode), so their DRAM latency overlaps

@@ -150,6 +150,35 @@ def test_gemm_narrow_tiles_are_invisible(M, N, K, taps):
     assert torch.equal(wide32, narrow32) and torch.equal(wide16, narrow16)
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K,taps", [(1000, 128, 128, 7), (517, 192, 192, 7), (2300, 384, 384, 7), (300, 384, 768, 3),
+                                         (700, 128, 64, 1), (40000, 192, 192, 1)])
+def test_gemm_encoder_tile_widths(prec, M, N, K, taps):
+    """N % 256 != 0 (the encoder's 128 / 192 / 384-channel convs) runs on 256 x 128 / 256 x 192 tiles; the
+    result matches the fp64 product and is bit-identical to the 256 x 64 tiling (same K order per element)."""
+    lib = _lib.load()
+    _, dt = PREC[prec]
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + taps)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dt)
+    w = (torch.randn(N, taps * K, device="cuda", generator=g) / (taps * K) ** 0.5).to(dt)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    try:
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(2))
+        n32 = gemm(prec, a, w, taps=taps, bias=bias, residual=res)
+        n16 = gemm(prec, a, w, taps=taps, out_fp32=False, bias=bias, act=1)
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(1))
+        w32 = gemm(prec, a, w, taps=taps, bias=bias, residual=res)
+        w16 = gemm(prec, a, w, taps=taps, out_fp32=False, bias=bias, act=1)
+    finally:
+        _lib.check(lib.b200codec_set_gemm_narrow_tiles(1))
+    ap = F.pad(a.double(), (0, 0, taps // 2, taps // 2))
+    cols = torch.cat([ap[t:t + M] for t in range(taps)], dim=1)  # [M, taps * K], tap-major like the weight
+    ref = cols @ w.double().t() + bias.double() + res.double()
+    assert (w32.double() - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(n32, w32) and torch.equal(n16, w16)
+
+
 # ----------------------------------------------------------------------------------------------
 # norms
 # ----------------------------------------------------------------------------------------------

@@ -1790,8 +1790,9 @@ int b200codec_set_istft_tile(int hops) {
     return 0;
 }
 
-int b200codec_set_gemm_narrow_tiles(int on) {
-    g_gemm_narrow_tiles = on != 0;
+int b200codec_set_gemm_narrow_tiles(int mode) {
+    B200_CHECK(mode >= 0 && mode <= 2, "narrow-tile mode must be 0 (256-wide only), 1 (default) or 2 (64-wide for every N %% 256 != 0)");
+    g_gemm_narrow_tiles = mode;
     return 0;
 }
 

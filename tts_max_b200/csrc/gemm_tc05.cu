@@ -337,18 +337,54 @@ int fill_maps_2cta(const GemmCall& c, int block_n, CUtensorMap* ta, CUtensorMap*
 }
 
 template <bool kChain>
-int launch_2cta(int precision, bool gn, bool narrow, const ChainMaps& maps, const ChainParams& cp, cudaStream_t s) {
+int launch_2cta(int precision, bool gn, int block_n, const ChainMaps& maps, const ChainParams& cp, cudaStream_t s) {
     const bool bf = precision == kPrecBf16;
-    if (narrow) {
+    if (block_n == 64) {
         if (gn) return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, true, 64, kChain>(maps, cp, s)
                           : launch_gemm_tc05_2cta<__half, true, 64, kChain>(maps, cp, s);
         return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, false, 64, kChain>(maps, cp, s)
                   : launch_gemm_tc05_2cta<__half, false, 64, kChain>(maps, cp, s);
     }
+    if constexpr (!kChain) {  // the encoder's channel widths: plain launches without GroupNorm statistics
+        if (block_n == 128 && !gn)
+            return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, false, 128, false>(maps, cp, s)
+                      : launch_gemm_tc05_2cta<__half, false, 128, false>(maps, cp, s);
+        if (block_n == 192 && !gn)
+            return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, false, 192, false>(maps, cp, s)
+                      : launch_gemm_tc05_2cta<__half, false, 192, false>(maps, cp, s);
+    }
+    B200_CHECK(block_n == 256, "gemm: no %d-wide instantiation for this launch", block_n);
     if (gn) return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, true, 256, kChain>(maps, cp, s)
                       : launch_gemm_tc05_2cta<__half, true, 256, kChain>(maps, cp, s);
     return bf ? launch_gemm_tc05_2cta<__nv_bfloat16, false, 256, kChain>(maps, cp, s)
               : launch_gemm_tc05_2cta<__half, false, 256, kChain>(maps, cp, s);
+}
+
+// Tile width of a CTA-pair GEMM whose N is not a multiple of 256 (the encoder's convs): the widest of
+// 192 / 128 / 64 that divides N, unless that leaves CTA pairs idle that a narrower tiling would use.
+// Cost per launch ~ rounds x (K blocks x time per K block + fixed), floored by the L2 traffic of re-reading
+// the A operand once per n-tile.
+int pick_block_n(const GemmCall& c) {
+    const int pairs = kNumSMs / 2;
+    const int m_blocks = (c.a_rows + 255) / 256;
+    const double kb = static_cast<double>(c.taps) * (c.Cin / 64);
+    int best = 64;
+    double best_cost = 1e30;
+    for (int bn : {64, 128, 192}) {
+        if (c.n_store % bn != 0) continue;
+        if (bn != 64 && (c.gn_stats != nullptr)) continue;
+        const int tiles = m_blocks * (c.n_store / bn);
+        const int rounds = (tiles + pairs - 1) / pairs;
+        const double t_kb = bn == 64 ? 0.15 : bn == 128 ? 0.16 : 0.20;          // us per 64-deep K block
+        const double t_tile = kb * t_kb + 2.0 + 0.012 * bn;                       // + prologue / epilogue
+        const double a_bytes = static_cast<double>(c.a_rows) * c.Cin * 2.0 * c.taps * (c.n_store / bn);
+        const double cost = std::max(rounds * t_tile, a_bytes / 6.0e6);           // ~6 TB/s from L2
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
 }
 
 }  // namespace
@@ -358,8 +394,9 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     if (fill_params(c, &p)) return 1;
     if (c.a_rows <= 0) return 0;
     if (gemm_kind(c) == kGemm2Cta) {
-        const bool narrow = c.n_store % 256 != 0 || (c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store));
-        const int block_n = narrow ? 64 : 256;
+        int block_n = 256;
+        if (c.n_store % 256 != 0) block_n = g_gemm_narrow_tiles == 2 ? 64 : pick_block_n(c);
+        else if (c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store)) block_n = 64;
         alignas(64) ChainMaps maps;
         ChainParams cp{};
         if (fill_maps_2cta(c, block_n, &maps.a[0], &maps.b[0], &maps.o32[0], &maps.o16[0])) return 1;
@@ -371,7 +408,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
         cp.counters = nullptr;
         cp.early_weights = g_gemm_early_weights;
         cp.g[0] = p;
-        return launch_2cta<false>(c.precision, p.gn_stats != nullptr, narrow, maps, cp, stream);
+        return launch_2cta<false>(c.precision, p.gn_stats != nullptr, block_n, maps, cp, stream);
     }
     const bool wide = gemm_is_wide(c);
     alignas(64) CUtensorMap ta, tb;
@@ -495,7 +532,7 @@ int launch_gemm_chain(const GemmCall* calls, int n, uint32_t* counters, cudaStre
         cp.tile_end[i] = end;
         cp.num_n[i] = 1;
     }
-    return launch_2cta<true>(calls[0].precision, false, narrow, maps, cp, stream);
+    return launch_2cta<true>(calls[0].precision, false, narrow ? 64 : 256, maps, cp, stream);
 }
 
 int launch_repack_weight(int prec, const float* src, void* dst, int N, int Cin, int taps,

@@ -137,8 +137,10 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
 // BLOCK_N: 256, or 64 for small M: with one to a few m-blocks only N / 256 of the 74 CTA pairs would
 // have a tile and each would walk the whole K loop alone; 256 x 64 tiles put four times as many pairs
 // to work (the K loop of a narrow tile is bounded by the A-tile load, ~0.15 us per K-block instead of
-// 0.26). Every output element sees the same K order, so the tile width never changes results. The
-// shared-memory stage keeps its 256-wide size; TMEM holds 2 x BLOCK_N columns.
+// 0.26). 128 / 192: the widths of the encoder's 96(128)-, 192- and 384-channel convs -- with 64-wide tiles
+// every n-tile re-reads the A operand from L2 once per tap (a 7-tap conv at N = 384: 42 times), which
+// made those launches L2-bandwidth-bound. Every output element sees the same K order, so the tile width
+// never changes results. The shared-memory stage keeps its 256-wide size; TMEM holds 2 x BLOCK_N columns.
 // ---------------------------------------------------------------------------------------------------
 // GEMM chains (kChain). Inside a transformer block c_proj -> fc1 -> fc2 -> (next block's) c_attn are
 // row-block local: RMSNorm is per row and already travels as sum-of-squares partials, so a 256-row block
@@ -205,13 +207,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams cp) {
     const GemmParams& p = cp.g[0];  // plain GEMM: the only one; chains: per-tile parameters are cp.g[g]
     using SM = Gemm2Smem;
-    static_assert(BLOCK_N == 256 || BLOCK_N == 64, "tile width");
+    static_assert(BLOCK_N == 256 || BLOCK_N == 192 || BLOCK_N == 128 || BLOCK_N == 64, "tile width");
     constexpr int kHalfN = BLOCK_N / 2;  // B rows staged by each CTA = accumulator columns per epilogue warp
     constexpr uint32_t kStageTx = 2 * (SM::kABytes + kHalfN * 128);  // bytes both CTAs land per stage
     constexpr int BLOCK_K = 64;
     constexpr int UMMA_K = 16;
     constexpr int kStages = kGemm2Stages;
-    constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages of BLOCK_N fp32 columns (512 or 128)
+    // two accumulator stages of BLOCK_N fp32 columns; allocations are powers of two (2 x 192 -> 512)
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 128 ? 128 : 2 * BLOCK_N <= 256 ? 256 : 512;
     static_assert(sizeof(InT) == 2, "2-CTA kernel is instantiated for bf16 / fp16 operands");
 
     extern __shared__ uint8_t smem_raw[];
