@@ -317,8 +317,17 @@ int b200enc_finalize_weights(B200Enc* h, void* stream);
 int b200enc_encode(B200Enc* h, const float* wav_dev, int64_t n_samples, const float* w2v_dev, void* ids_dev,
                    int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev, float* semantic_dev,
                    void* stream);
+/* A batch of n_clips equally long clips in ONE launch sequence (80 kernels; reference: Encoder.forward on a
+ * (B, 1, S) tensor, encoder.py:58-71): wav_dev [n_clips][n_samples], w2v_dev [n_clips][T][1024], ids
+ * [n_clips][T], hidden_dev [n_clips][T][2048], acoustic_dev / semantic_dev [n_clips][T][1024]. The clips share a
+ * padded row space; zero gap rows between them are the convolutions' zero padding, so every clip's result is
+ * the one b200enc_encode gives for it alone. n_clips x (n_samples + 1920) must stay below 2^31. */
+int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t n_samples, const float* w2v_dev,
+                         void* ids_dev, int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev,
+                         float* semantic_dev, void* stream);
 /* stage parity: with taps on, every encode keeps conv_blocks[0 .. 5] outputs ("conv0", "block1" .. "block5");
- * read_stage returns one as fp32 token-major [rows][C] (rows = n_samples / stride so far, C = 48 * 2^i) */
+ * read_stage returns one as fp32 token-major [clips][rows][C] (rows = n_samples / stride so far, C = 48 * 2^i;
+ * clips = those of the last encode call) */
 int b200enc_set_stage_taps(B200Enc* h, int on);
 int b200enc_read_stage(B200Enc* h, const char* name, int64_t n_samples, float* host_out, size_t n_elems,
                        void* stream);

@@ -121,10 +121,10 @@ def test_gpu_encoder_vs_reference_golden(gpu_encoders, egolden, esd, prec, name)
         enc.set_stage_taps(True)
     try:
         code, aux = enc(wav.cuda(), w2v.cuda(), return_hidden=True)
-        if name == "b2x12":   # taps hold the LAST utterance of the batch
+        if name == "b2x12":   # taps hold every clip of the batch: (B, rows, C)
             for key, floor in (("conv0", 100.0), ("block1", SNR_MIN[prec]), ("block3", SNR_MIN[prec]), ("block5", SNR_MIN[prec])):
                 got = enc.read_stage(key, S)
-                ref = torch.from_numpy(egolden[f"{name}_{key}"])[B - 1].t()
+                ref = torch.from_numpy(egolden[f"{name}_{key}"]).transpose(1, 2)
                 assert got.shape == ref.shape, (key, got.shape, ref.shape)
                 snr = O.snr_db(ref, got)
                 print(f"[enc stage] {key} {prec}: SNR {snr:.1f} dB")
@@ -154,15 +154,26 @@ def test_gpu_encoder_vs_reference_golden(gpu_encoders, egolden, esd, prec, name)
 
 @pytest.mark.gpu
 def test_gpu_encoder_batch_equals_single_and_round_trip(gpu_encoders, gpu_decoders):
-    """A batch is a loop over utterances (identical results), a 4 s utterance runs at full rate counts, and the
-    ids feed the decoder: wav (1, S) -> T = ceil-ish(S / 320) tokens -> 320 T samples (encode -> decode plumbing)."""
+    """The clips of a batch share one launch sequence and one padded row space; every clip's ids AND hidden states
+    are bit-identical to encoding it alone (also when the batch is split into groups). A 4 s utterance runs at
+    full rate counts, and the ids feed the decoder: wav (1, S) -> T = ceil-ish(S / 320) tokens -> 320 T samples."""
     enc = gpu_encoders["bf16"]
     g = torch.Generator().manual_seed(5)
-    wav = 0.3 * torch.randn(3, 1, 320 * 40, generator=g)
-    w2v = torch.randn(3, 40, 1024, generator=g)
-    batch = enc(wav.cuda(), w2v.cuda())
-    for b in range(3):
-        assert torch.equal(enc(wav[b:b + 1].cuda(), w2v[b:b + 1].cuda()), batch[b:b + 1])
+    wav = 0.3 * torch.randn(5, 1, 320 * 40, generator=g)
+    w2v = torch.randn(5, 40, 1024, generator=g)
+    batch, aux = enc(wav.cuda(), w2v.cuda(), return_hidden=True)
+    for b in range(5):
+        one, aux1 = enc(wav[b:b + 1].cuda(), w2v[b:b + 1].cuda(), return_hidden=True)
+        assert torch.equal(one, batch[b:b + 1])
+        for key in ("hidden", "acoustic", "semantic"):
+            assert torch.equal(aux1[key], aux[key][b:b + 1]), (b, key)
+    saved = enc.max_batch_samples
+    try:
+        enc.max_batch_samples = 2 * (320 * 40 + 1920)   # groups of 2, 2, 1 clips
+        split, aux2 = enc(wav.cuda(), w2v.cuda(), return_hidden=True)
+    finally:
+        enc.max_batch_samples = saved
+    assert torch.equal(split, batch) and torch.equal(aux2["hidden"], aux["hidden"])
     long_wav = 0.3 * torch.randn(1, 64000 - 77, generator=g)            # Encoder.encode pads to 64000
     ids = enc.encode(long_wav, torch.randn(1, 200, 1024, generator=g))
     assert ids.shape == (200,) and ids.min() >= 0 and ids.max() < 65536

@@ -93,6 +93,8 @@ SIGNATURES = {
     "b200enc_finalize_weights": (c_int, [c_void_p, c_void_p]),
     "b200enc_encode": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
+    "b200enc_encode_batch": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
     "b200enc_set_stage_taps": (c_int, [c_void_p, c_int]),
     "b200enc_read_stage": (c_int, [c_void_p, c_char_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "b200enc_launch_count": (c_int64, [c_void_p]),

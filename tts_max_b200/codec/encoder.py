@@ -145,6 +145,9 @@ class Encoder(torch.nn.Module):
         self._handle: ctypes.c_void_p | None = None
         self._device = torch.device("cpu")
         self._dirty = True
+        self._tap_clips = 0
+        # clips of one forward() are encoded in groups of at most this many samples (~3 KB of workspace per sample)
+        self.max_batch_samples = 4_000_000
         if model_path is not None:
             self.load_from_checkpoint(model_path)
 
@@ -246,7 +249,8 @@ class Encoder(torch.nn.Module):
     @torch.no_grad()
     def forward(self, wavs: torch.Tensor, w2v_hidden: torch.Tensor, return_hidden: bool = False):
         """Computes VQ codes for a batch of audio (reference: encoder.py:58-71 with `wav2vec_model(...)
-        .hidden_states[16]` passed in). Utterances of a batch are encoded one launch sequence each."""
+        .hidden_states[16]` passed in). The clips of a batch share one launch sequence (80 kernels): they sit
+        in one padded row space, separated by zero gap rows that act as the convolutions' zero padding."""
         if wavs.dim() != 3 or wavs.shape[1] != 1:
             raise ValueError(f"wavs must be (batch, 1, samples), got {tuple(wavs.shape)}")
         b, _, s = wavs.shape
@@ -265,14 +269,18 @@ class Encoder(torch.nn.Module):
             acoustic = torch.empty(b, t, 1024, dtype=torch.float32, device=self._device) if return_hidden else None
             semantic = torch.empty(b, t, 1024, dtype=torch.float32, device=self._device) if return_hidden else None
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            for i in range(b):
-                _lib.check(lib.b200enc_encode(
-                    handle, ctypes.c_void_p(wavs[i].data_ptr()), s, ctypes.c_void_p(w2v_hidden[i].data_ptr()),
+            # one launch sequence per group of clips; a group is bounded by `max_batch_samples` of workspace
+            group = max(1, min(b, self.max_batch_samples // (s + 6 * _HOP_LENGTH)))
+            for i in range(0, b, group):
+                n = min(group, b - i)
+                _lib.check(lib.b200enc_encode_batch(
+                    handle, ctypes.c_void_p(wavs[i].data_ptr()), n, s, ctypes.c_void_p(w2v_hidden[i].data_ptr()),
                     ctypes.c_void_p(ids[i].data_ptr()), _lib.IDS_I32, 1 if self._pre_bound else 0,
                     ctypes.c_void_p(hidden[i].data_ptr()) if hidden is not None else None,
                     ctypes.c_void_p(acoustic[i].data_ptr()) if acoustic is not None else None,
                     ctypes.c_void_p(semantic[i].data_ptr()) if semantic is not None else None,
                     ctypes.c_void_p(stream)))
+                self._tap_clips = n
         vq_code = ids.view(b, t, 1).permute(0, 2, 1)     # (B, 1, T), like Encoder.quantize (encoder.py:73-78)
         if return_hidden:
             return vq_code, {"hidden": hidden.permute(0, 2, 1), "acoustic": acoustic.permute(0, 2, 1),
@@ -298,18 +306,20 @@ class Encoder(torch.nn.Module):
         _lib.check(_lib.load().b200enc_set_stage_taps(self._ensure_handle(), 1 if on else 0))
 
     def read_stage(self, name: str, n_samples: int) -> torch.Tensor:
-        """fp32 (rows, C) copy of conv_blocks[i]'s output of the LAST encoded utterance ("conv0", "block1".."block5")."""
+        """fp32 copy of conv_blocks[i]'s output of the LAST launch sequence ("conv0", "block1".."block5"): (rows, C)
+        when it encoded one clip, (clips, rows, C) for a group of clips."""
         idx = 0 if name == "conv0" else int(name[len("block"):])
         rows, c = n_samples, 48
         for stride in (2, 2, 4, 4, 5)[:idx]:
             rows //= stride
             c *= 2
-        out = torch.empty(rows, c, dtype=torch.float32)
+        clips = max(1, self._tap_clips)
+        out = torch.empty(clips, rows, c, dtype=torch.float32)
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(_lib.load().b200enc_read_stage(self._ensure_handle(), name.encode(), n_samples,
                                                       ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.c_void_p(stream)))
-        return out
+        return out[0] if clips == 1 else out
 
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_lib.load().b200enc_launch_count(self._handle))

@@ -66,10 +66,11 @@ struct Buf {
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// conv_blocks[0]: Conv1d(1 -> 48, k = 7, padding 3), weight-normed: x0[t, c] = b[c] + sum_k w[c][k] wav[t + k - 3]
+// conv_blocks[0]: Conv1d(1 -> 48, k = 7, padding 3), weight-normed: x0[t, c] = b[c] + sum_k w[c][k] wav[t + k - 3].
+// blockIdx.y = clip: wav is compact [clips][S], out is the slotted row space (clip b at row b * slot).
 __global__ void __launch_bounds__(256)
-enc_conv0_kernel(const float* __restrict__ wav, int S, const float* __restrict__ w /*[C][7]*/,
-                 const float* __restrict__ bias, int C, int P, float* __restrict__ out /*[S][P]*/) {
+enc_conv0_kernel(const float* __restrict__ wav, int S, int slot, const float* __restrict__ w /*[C][7]*/,
+                 const float* __restrict__ bias, int C, int P, float* __restrict__ out /*[clips * slot][P]*/) {
     pdl_launch_dependents();
     pdl_wait();
     // a thread owns 4 channels of one sample (128-bit stores); P / 4 threads per sample
@@ -77,6 +78,8 @@ enc_conv0_kernel(const float* __restrict__ wav, int S, const float* __restrict__
     const int c0 = (threadIdx.x % tpr) * 4;
     const int t = blockIdx.x * (blockDim.x / tpr) + threadIdx.x / tpr;
     if (t >= S) return;
+    wav += static_cast<size_t>(blockIdx.y) * S;
+    out += static_cast<size_t>(blockIdx.y) * slot * P;
     float xin[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -106,6 +109,9 @@ enc_conv0_kernel(const float* __restrict__ wav, int S, const float* __restrict__
 //   y[t]    = sum_k fd[k] s[clamp(2t + k - 5, 0, 2T - 1)]                            (k = 0..11)
 // A thread owns one channel and kSnakeRows consecutive rows: the 2 * rows + 10 snake values it needs live in
 // registers, consecutive threads are consecutive channels (coalesced 128-byte row segments).
+// Batches: blockIdx.z = clip, clip b occupies rows [b * slot, b * slot + T) of x and out; the slot - T gap rows
+// behind every clip are written as ZEROS -- they are the zero padding of the convolution that reads `out`
+// (its taps reach at most 27 rows across a clip edge; the gap is at least 30 rows at every level).
 constexpr int kSnakeRows = 16;
 
 struct SnakeFilters {
@@ -115,7 +121,7 @@ struct SnakeFilters {
 
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restrict__ alpha /*[P] e^alpha*/,
+snake_aa_kernel(const float* __restrict__ x, int T, int slot, int P, const float* __restrict__ alpha /*[P] e^alpha*/,
                 const float* __restrict__ inv_beta /*[P] 1 / (e^beta + 1e-9)*/, SnakeFilters f,
                 OutT* __restrict__ out) {
     pdl_launch_dependents();
@@ -123,7 +129,13 @@ snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restri
     constexpr int K = kSnakeRows;
     const int c = blockIdx.y * 64 + (threadIdx.x & 63);
     const int t0 = (blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6)) * K;
-    if (t0 >= T || c >= P) return;
+    if (t0 >= slot || c >= P) return;
+    x += static_cast<size_t>(blockIdx.z) * slot * P;
+    out += static_cast<size_t>(blockIdx.z) * slot * P;
+    if (t0 >= T) {  // a chunk of gap rows only
+        for (int r = 0; r < K && t0 + r < slot; ++r) out[static_cast<size_t>(t0 + r) * P + c] = Half16<OutT>::from_float(0.f);
+        return;
+    }
     const float a = alpha[c], ib = inv_beta[c];
     auto snake = [&](float u) {
         // sin via MUFU after a two-term Cody-Waite reduction of the argument to [-pi, pi]
@@ -187,20 +199,34 @@ snake_aa_kernel(const float* __restrict__ x, int T, int P, const float* __restri
     }
 #pragma unroll
     for (int r = 0; r < K; ++r) {
-        if (t0 + r >= T) break;
+        if (t0 + r >= slot) break;
         float y = 0.f;
 #pragma unroll
         for (int k = 0; k < 12; ++k) y = fmaf(f.down[k], sv[2 * r + k], y);
-        out[static_cast<size_t>(t0 + r) * P + c] = Half16<OutT>::from_float(y);
+        out[static_cast<size_t>(t0 + r) * P + c] = Half16<OutT>::from_float(t0 + r < T ? y : 0.f);
     }
 }
 
+// w2v hidden state: compact fp32 [clips][T][C] -> operand dtype in the slotted row space [clips * slot][C], gap rows
+// zero; also writes the row-validity bytes the token-level GEMM epilogues use to keep gap rows zero
 template <typename OutT>
-__global__ void cast_kernel(const float* __restrict__ x, size_t n, OutT* __restrict__ out) {
+__global__ void cast_slotted_kernel(const float* __restrict__ x, int T, int slot, int C, OutT* __restrict__ out,
+                                    uint8_t* __restrict__ row_valid) {
     pdl_launch_dependents();
     pdl_wait();
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        out[i] = Half16<OutT>::from_float(x[i]);
+    const int row = blockIdx.x;               // slotted row
+    const int clip = row / slot, pos = row - clip * slot;
+    const bool ok = pos < T;
+    if (threadIdx.x == 0) row_valid[row] = ok ? 1 : 0;
+    const float4* src = reinterpret_cast<const float4*>(x + (static_cast<size_t>(clip) * T + pos) * C);
+    OutT* dst = out + static_cast<size_t>(row) * C;
+    for (int i = threadIdx.x; i < C / 4; i += blockDim.x) {
+        const float4 v = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 pk;
+        pk.x = Half16<OutT>::pack(v.x, v.y);
+        pk.y = Half16<OutT>::pack(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
+    }
 }
 
 // weight-normed Conv1d weight [Cout][Cin][k] (scale[Cout] = g / ||v||) -> GEMM operand [Npad][k * Cinpad], zero padded
@@ -299,9 +325,11 @@ struct B200Enc {
     ConvW conv_final;
     ConvW sem_init, sem_rb1, sem_rb3, sem_final, fusion;
 
-    // workspace for one utterance of up to ws_samples samples
+    // workspace for a batch of up to ws_samples slotted samples (clips x (samples + gap))
     Buf ws;
     int64_t ws_samples = 0;
+    uint8_t* row_valid = nullptr;  // [token rows] 1 on a clip's tokens, 0 on gap rows
+    void* ids_tmp = nullptr;       // [token rows] ids in the slotted row space (int64 sized)
     float* x[kStages + 1];   // fp32 [R_i][P_i]
     float* hb[kStages];      // fp32 conv7 output
     void* a[kStages + 1];    // operand [R_i][P_i]
@@ -316,6 +344,7 @@ struct B200Enc {
     bool taps_on = false;
     Buf tap[kStages + 1];
     int64_t tap_samples = 0;
+    int tap_clips = 0;
 
     const float* m(const std::string& key) const {
         auto it = index.find(key);
@@ -401,20 +430,20 @@ int repack_strided(const float* v, const float* scale, void* dst, int Cout, int 
     return 0;
 }
 
-int snake(B200Enc* h, const float* x, int T, int P, const ActW& w, void* out, cudaStream_t s) {
+int snake(B200Enc* h, const float* x, int T, int slot, int clips, int P, const ActW& w, void* out, cudaStream_t s) {
     const int row_groups = 256 / 64;  // 4 row chunks per CTA
-    dim3 grid((T + kSnakeRows * row_groups - 1) / (kSnakeRows * row_groups), P / 64);
+    dim3 grid((slot + kSnakeRows * row_groups - 1) / (kSnakeRows * row_groups), P / 64, clips);
     if (h->precision == kPrecBf16)
-        B200_CUDA_OK(launch_kernel(snake_aa_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, x, T, P, w.alpha, w.inv_beta, w.f,
+        B200_CUDA_OK(launch_kernel(snake_aa_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, x, T, slot, P, w.alpha, w.inv_beta, w.f,
                                    static_cast<__nv_bfloat16*>(out)));
     else
-        B200_CUDA_OK(launch_kernel(snake_aa_kernel<__half>, grid, dim3(256), 0, s, x, T, P, w.alpha, w.inv_beta, w.f,
+        B200_CUDA_OK(launch_kernel(snake_aa_kernel<__half>, grid, dim3(256), 0, s, x, T, slot, P, w.alpha, w.inv_beta, w.f,
                                    static_cast<__half*>(out)));
     return 0;
 }
 
 GemmCall conv_call(B200Enc* h, const void* a, int rows, int Cin, const ConvW& w, int N, int taps, int dil, void* out,
-                   bool out_fp32, int ldc, const float* residual, int act) {
+                   bool out_fp32, int ldc, const float* residual, int act, const uint8_t* row_valid = nullptr) {
     GemmCall c{};
     c.precision = h->precision;
     c.a = a;
@@ -432,14 +461,21 @@ GemmCall conv_call(B200Enc* h, const void* a, int rows, int Cin, const ConvW& w,
     c.bias = w.bias;
     c.residual = residual;
     c.ld_res = ldc;
-    c.row_valid = nullptr;
+    c.row_valid = row_valid;
     c.act = act;
     c.out16_scale = 1.f;
     c.ss_in_scale = 1.f;
     return c;
 }
 
-int ensure_ws(B200Enc* h, int64_t S) {
+// Batches: the clips of one call (all n_samples long) sit in ONE slotted row space. Clip b owns rows
+// [b * slot_l, b * slot_l + T_l) at level l; behind every clip there are kGapTokens tokens' worth of gap rows
+// (6 tokens = 1920 samples: 30 rows at the 250 Hz level, where a dilation-9 conv reaches 27 rows) that the
+// snake kernel writes as zeros, so a convolution's taps read zero padding across a clip edge. slot_l is a
+// multiple of every later stride, so the [rows / s, s * C] super-row view of the strided convs stays aligned.
+constexpr int kGapTokens = 6;
+
+int ensure_ws(B200Enc* h, int64_t S) {  // S: slotted samples of the whole batch
     if (S <= h->ws_samples) return 0;
     const size_t es = 2;
     const int64_t T = S / kHopTotal;
@@ -464,6 +500,8 @@ int ensure_ws(B200Enc* h, int64_t S) {
     const size_t o_ac = total; total += sz32;
     const size_t o_sem = total; total += sz32;
     const size_t o_hid = total; total += 2 * sz32;
+    const size_t o_valid = total; total += al(static_cast<size_t>(T));
+    const size_t o_ids = total; total += al(static_cast<size_t>(T) * 8);
     h->ws_samples = 0;
     if (h->ws.ensure(total)) return 1;
     B200_CUDA_OK(cudaMemset(h->ws.p, 0, h->ws.bytes));
@@ -478,7 +516,8 @@ int ensure_ws(B200Enc* h, int64_t S) {
     h->cat16 = p + o_cat;
     h->ac32 = reinterpret_cast<float*>(p + o_ac); h->sem32 = reinterpret_cast<float*>(p + o_sem);
     h->hid32 = reinterpret_cast<float*>(p + o_hid);
-    // the workspace is sized for (S + S / 4) samples by Buf::ensure's slack only in bytes; rows are bounded by S
+    h->row_valid = p + o_valid;
+    h->ids_tmp = p + o_ids;
     h->ws_samples = S;
     return 0;
 }
@@ -682,103 +721,130 @@ int b200enc_finalize_weights(B200Enc* h, void* stream) {
     return 0;
 }
 
-// Encoder.forward (encoder.py:58-78) for ONE utterance, the w2v-BERT hidden state given:
-//   wav_dev [n_samples] fp32 (n_samples a positive multiple of 320: Encoder.encode pads to that, :116-120),
-//   w2v_dev [T][1024] fp32 token-major, T = n_samples / 320  ->  ids [T].
-// hidden_dev [T][2048] / acoustic_dev [T][1024] / semantic_dev [T][1024] (fp32, optional) receive the fused
-// hidden state and the two encoders' outputs. Asynchronous on `stream`.
-int b200enc_encode(B200Enc* h, const float* wav_dev, int64_t n_samples, const float* w2v_dev, void* ids_dev,
-                   int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev, float* semantic_dev, void* stream) {
+// Encoder.forward for a batch of equally long clips (encoder.py:58-78):
+//   wav_dev [n_clips][n_samples] fp32 (n_samples a positive multiple of 320: Encoder.encode pads to that, :116-120),
+//   w2v_dev [n_clips][T][1024] fp32 token-major, T = n_samples / 320  ->  ids [n_clips][T].
+// hidden_dev [n_clips][T][2048] / acoustic_dev, semantic_dev [n_clips][T][1024] (fp32, optional) receive the fused
+// hidden state and the two encoders' outputs. One launch sequence for the whole batch (80 kernels), asynchronous
+// on `stream`.
+int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t n_samples, const float* w2v_dev,
+                         void* ids_dev, int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev,
+                         float* semantic_dev, void* stream) {
     B200_CHECK(h && wav_dev && w2v_dev, "b200enc_encode: null argument");
     B200_CHECK(h->finalized, "b200enc_encode called before b200enc_finalize_weights");
+    B200_CHECK(n_clips > 0 && n_clips <= 65535, "encode: n_clips (%d) must be in [1, 65535]", n_clips);
     B200_CHECK(n_samples > 0 && n_samples % kHopTotal == 0 && n_samples < (1ll << 30),
                "encode: n_samples (%lld) must be a positive multiple of 320", (long long)n_samples);
     B200_CHECK(ids_dev == nullptr || id_type == 0 || id_type == 1, "encode: id_type must be 0 (int32) or 1 (int64)");
+    const int S = static_cast<int>(n_samples), T = S / kHopTotal;
+    const int slot_tok = T + kGapTokens;
+    const int64_t total = static_cast<int64_t>(n_clips) * slot_tok * kHopTotal;  // slotted samples of the batch
+    B200_CHECK(total < (1ll << 31), "encode: batch too large (%d clips x %lld samples); split it", n_clips, (long long)n_samples);
     std::lock_guard<std::mutex> lock(h->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200_CUDA_OK(cudaSetDevice(h->device));
-    if (n_samples > h->ws_samples) {
+    if (total > h->ws_samples) {
         B200_CUDA_OK(cudaStreamSynchronize(s));  // the old workspace may still be in use
-        if (ensure_ws(h, n_samples)) return 1;
+        if (ensure_ws(h, total)) return 1;
     }
-    const int S = static_cast<int>(n_samples), T = S / kHopTotal;
     const bool bf = h->precision == kPrecBf16;
+    const int Rtok = n_clips * slot_tok;  // token-level rows
 
     // ---- acoustic encoder ----
-    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 15) / 16), dim3(256), 0, s, wav_dev, S, (const float*)h->conv0_w,
-                               (const float*)h->conv0_b, kGenFeatures, 64, h->x[0]));
+    int rows = S, slot = slot_tok * kHopTotal, c = kGenFeatures;  // valid rows per clip / rows per slot at this level
+    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 15) / 16, n_clips), dim3(256), 0, s, wav_dev, S, slot,
+                               (const float*)h->conv0_w, (const float*)h->conv0_b, kGenFeatures, 64, h->x[0]));
     h->launches++;
-    auto take_tap = [&](int idx, int64_t r, int Pc) -> int {
+    auto take_tap = [&](int idx, int64_t slot_rows, int Pc) -> int {
         if (!h->taps_on) return 0;
-        const size_t bytes = static_cast<size_t>(r) * Pc * 4;
+        const size_t bytes = static_cast<size_t>(n_clips) * slot_rows * Pc * 4;
         if (h->tap[idx].ensure(bytes)) return 1;
         B200_CUDA_OK(cudaMemcpyAsync(h->tap[idx].p, h->x[idx], bytes, cudaMemcpyDeviceToDevice, s));
         h->tap_samples = n_samples;
+        h->tap_clips = n_clips;
         return 0;
     };
-    if (take_tap(0, S, 64)) return 1;
-    int rows = S, c = kGenFeatures;
+    if (take_tap(0, slot, 64)) return 1;
     for (int i = 0; i < kStages; ++i) {
         const StageW& st = h->stage[i];
         const int P = pad64(c);
+        const int R = n_clips * slot;
         for (int u = 0; u < 3; ++u) {
-            ENC_RUN(snake(h, h->x[i], rows, P, st.unit[u].act0, h->a[i], s));
-            ENC_RUN(launch_gemm(conv_call(h, h->a[i], rows, P, st.unit[u].conv7, P, 7, kDil[u], h->hb[i], true, P, nullptr, kActNone), s));
-            ENC_RUN(snake(h, h->hb[i], rows, P, st.unit[u].act2, h->a[i], s));
-            ENC_RUN(launch_gemm(conv_call(h, h->a[i], rows, P, st.unit[u].conv1, P, 1, 1, h->x[i], true, P, h->x[i], kActNone), s));
+            ENC_RUN(snake(h, h->x[i], rows, slot, n_clips, P, st.unit[u].act0, h->a[i], s));
+            ENC_RUN(launch_gemm(conv_call(h, h->a[i], R, P, st.unit[u].conv7, P, 7, kDil[u], h->hb[i], true, P, nullptr, kActNone), s));
+            ENC_RUN(snake(h, h->hb[i], rows, slot, n_clips, P, st.unit[u].act2, h->a[i], s));
+            ENC_RUN(launch_gemm(conv_call(h, h->a[i], R, P, st.unit[u].conv1, P, 1, 1, h->x[i], true, P, h->x[i], kActNone), s));
         }
-        ENC_RUN(snake(h, h->x[i], rows, P, st.act, h->a[i], s));
+        ENC_RUN(snake(h, h->x[i], rows, slot, n_clips, P, st.act, h->a[i], s));
         const int sdn = kStrides[i], P2 = pad64(2 * c);
         // the same operand buffer viewed as [rows / s][s * P]: a 3-tap conv over super-rows
-        ENC_RUN(launch_gemm(conv_call(h, h->a[i], rows / sdn, sdn * P, st.down, P2, 3, 1, h->x[i + 1], true, P2, nullptr, kActNone), s));
+        ENC_RUN(launch_gemm(conv_call(h, h->a[i], R / sdn, sdn * P, st.down, P2, 3, 1, h->x[i + 1], true, P2, nullptr, kActNone), s));
         rows /= sdn;
+        slot /= sdn;
         c *= 2;
-        if (take_tap(i + 1, rows, P2)) return 1;
+        if (take_tap(i + 1, slot, P2)) return 1;
     }
     const size_t es = 2;
+    // ---- semantic encoder input: cast into the slotted token rows (also writes the row-validity bytes) ----
+    if (bf) B200_CUDA_OK(launch_kernel(cast_slotted_kernel<__nv_bfloat16>, dim3(Rtok), dim3(256), 0, s, w2v_dev, T, slot_tok, 1024,
+                                       static_cast<__nv_bfloat16*>(h->s16a), h->row_valid));
+    else B200_CUDA_OK(launch_kernel(cast_slotted_kernel<__half>, dim3(Rtok), dim3(256), 0, s, w2v_dev, T, slot_tok, 1024,
+                                    static_cast<__half*>(h->s16a), h->row_valid));
+    h->launches++;
     {
         const int P = pad64(c);  // 1536
-        ENC_RUN(snake(h, h->x[kStages], rows, P, h->act_final, h->a[kStages], s));
-        GemmCall g = conv_call(h, h->a[kStages], rows, P, h->conv_final, kOutDim, 3, 1, h->ac32, true, kOutDim, nullptr, kActNone);
+        ENC_RUN(snake(h, h->x[kStages], rows, slot, n_clips, P, h->act_final, h->a[kStages], s));
+        GemmCall g = conv_call(h, h->a[kStages], Rtok, P, h->conv_final, kOutDim, 3, 1, h->ac32, true, kOutDim, nullptr, kActNone);
         g.out16 = static_cast<uint8_t*>(h->cat16) + 1024 * es;  // right half of [semantic | acoustic]
         g.ld16 = 2048;
         ENC_RUN(launch_gemm(g, s));
     }
-    // ---- semantic encoder (encoder_modules.py:121-125; ReLU(inplace=True) makes the skip carry relu(x)) ----
+    // ---- semantic encoder (encoder_modules.py:121-125; ReLU(inplace=True) makes the skip carry relu(x)). The
+    // outputs that feed the next 3-tap conv keep their gap rows zero (row_valid), like the decoder's halo rows ----
     {
-        const size_t n = static_cast<size_t>(T) * 1024;
-        const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
-        if (bf) B200_CUDA_OK(launch_kernel(cast_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, w2v_dev, n, static_cast<__nv_bfloat16*>(h->s16a)));
-        else B200_CUDA_OK(launch_kernel(cast_kernel<__half>, dim3(grid), dim3(256), 0, s, w2v_dev, n, static_cast<__half*>(h->s16a)));
-        h->launches++;
-        GemmCall g0 = conv_call(h, h->s16a, T, 1024, h->sem_init, 1024, 3, 1, h->sr, true, 1024, nullptr, kActRelu);
+        const uint8_t* rv = h->row_valid;
+        GemmCall g0 = conv_call(h, h->s16a, Rtok, 1024, h->sem_init, 1024, 3, 1, h->sr, true, 1024, nullptr, kActRelu, rv);
         g0.out16 = h->s16b;  // r = relu(initial_conv(x)) as fp32 (skip) and as operand
         g0.ld16 = 1024;
         ENC_RUN(launch_gemm(g0, s));
-        ENC_RUN(launch_gemm(conv_call(h, h->s16b, T, 1024, h->sem_rb1, 1024, 3, 1, h->s16a, false, 1024, nullptr, kActRelu), s));
-        GemmCall g2 = conv_call(h, h->s16a, T, 1024, h->sem_rb3, 1024, 3, 1, h->sx, true, 1024, h->sr, kActNone);
+        ENC_RUN(launch_gemm(conv_call(h, h->s16b, Rtok, 1024, h->sem_rb1, 1024, 3, 1, h->s16a, false, 1024, nullptr, kActRelu, rv), s));
+        GemmCall g2 = conv_call(h, h->s16a, Rtok, 1024, h->sem_rb3, 1024, 3, 1, h->sx, true, 1024, h->sr, kActNone, rv);
         g2.out16 = h->s16b;
         g2.ld16 = 1024;
         ENC_RUN(launch_gemm(g2, s));
-        GemmCall g3 = conv_call(h, h->s16b, T, 1024, h->sem_final, 1024, 3, 1, h->sem32, true, 1024, nullptr, kActNone);
+        GemmCall g3 = conv_call(h, h->s16b, Rtok, 1024, h->sem_final, 1024, 3, 1, h->sem32, true, 1024, nullptr, kActNone);
         g3.out16 = h->cat16;  // left half of [semantic | acoustic]
         g3.ld16 = 2048;
         ENC_RUN(launch_gemm(g3, s));
     }
     // ---- fusion + quantise ----
-    ENC_RUN(launch_gemm(conv_call(h, h->cat16, T, 2048, h->fusion, 2048, 1, 1, h->hid32, true, 2048, nullptr, kActNone), s));
+    ENC_RUN(launch_gemm(conv_call(h, h->cat16, Rtok, 2048, h->fusion, 2048, 1, 1, h->hid32, true, 2048, nullptr, kActNone), s));
+    // results leave the slotted row space: one strided copy per output (clip b: rows [b * slot_tok, b * slot_tok + T))
+    auto compact = [&](void* dst, const void* src, size_t row_bytes) -> int {
+        B200_CUDA_OK(cudaMemcpy2DAsync(dst, static_cast<size_t>(T) * row_bytes, src, static_cast<size_t>(slot_tok) * row_bytes,
+                                       static_cast<size_t>(T) * row_bytes, static_cast<size_t>(n_clips), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    };
     if (ids_dev != nullptr) {
-        ENC_RUN(launch_fsq_quantize(h->hid32, 2048, T, h->m("quantizer.project_in.weight"), h->m("quantizer.project_in.bias"),
-                                    2048, pre_bound, ids_dev, id_type, nullptr, s));
+        ENC_RUN(launch_fsq_quantize(h->hid32, 2048, Rtok, h->m("quantizer.project_in.weight"), h->m("quantizer.project_in.bias"),
+                                    2048, pre_bound, h->ids_tmp, id_type, nullptr, s));
+        if (compact(ids_dev, h->ids_tmp, id_type == 1 ? 8 : 4)) return 1;
     }
-    if (hidden_dev) B200_CUDA_OK(cudaMemcpyAsync(hidden_dev, h->hid32, static_cast<size_t>(T) * 2048 * 4, cudaMemcpyDeviceToDevice, s));
-    if (acoustic_dev) B200_CUDA_OK(cudaMemcpyAsync(acoustic_dev, h->ac32, static_cast<size_t>(T) * 1024 * 4, cudaMemcpyDeviceToDevice, s));
-    if (semantic_dev) B200_CUDA_OK(cudaMemcpyAsync(semantic_dev, h->sem32, static_cast<size_t>(T) * 1024 * 4, cudaMemcpyDeviceToDevice, s));
+    if (hidden_dev && compact(hidden_dev, h->hid32, 2048 * 4)) return 1;
+    if (acoustic_dev && compact(acoustic_dev, h->ac32, 1024 * 4)) return 1;
+    if (semantic_dev && compact(semantic_dev, h->sem32, 1024 * 4)) return 1;
     return 0;
 }
 
-// Debug / stage parity: fp32 copy of an acoustic-encoder stage of the LAST encode, token-major [rows][C]
-// (pad channels dropped): "conv0" (S rows, 48), "block1".."block5" (EncoderBlock outputs: rows S/2 .. S/320).
+// One clip: Encoder.forward on [1, 1, n_samples] (kept for callers of ABI 3's first encode entry).
+int b200enc_encode(B200Enc* h, const float* wav_dev, int64_t n_samples, const float* w2v_dev, void* ids_dev,
+                   int id_type, int pre_bound, float* hidden_dev, float* acoustic_dev, float* semantic_dev, void* stream) {
+    return b200enc_encode_batch(h, wav_dev, 1, n_samples, w2v_dev, ids_dev, id_type, pre_bound, hidden_dev, acoustic_dev,
+                                semantic_dev, stream);
+}
+
+// Debug / stage parity: fp32 copy of an acoustic-encoder stage of the LAST encode, [clips][rows][C] token-major
+// (pad channels and gap rows dropped): "conv0" (S rows, 48), "block1".."block5" (EncoderBlock outputs: rows S/2 .. S/320).
 int b200enc_read_stage(B200Enc* h, const char* name, int64_t n_samples, float* host_out, size_t n_elems, void* stream) {
     B200_CHECK(h && name && host_out, "b200enc_read_stage: null argument");
     std::lock_guard<std::mutex> lock(h->mu);
@@ -788,19 +854,24 @@ int b200enc_read_stage(B200Enc* h, const char* name, int64_t n_samples, float* h
     if (std::strcmp(name, "conv0") == 0) idx = 0;
     else if (std::strncmp(name, "block", 5) == 0 && name[5] >= '1' && name[5] <= '5' && name[6] == 0) idx = name[5] - '0';
     B200_CHECK(idx >= 0, "read_stage: unknown stage \"%s\"", name);
-    int64_t rows = n_samples;
+    int64_t rows = n_samples, slot = (n_samples / kHopTotal + kGapTokens) * kHopTotal;
     int c = kGenFeatures;
     for (int i = 0; i < idx; ++i) {
         rows /= kStrides[i];
+        slot /= kStrides[i];
         c *= 2;
     }
     const int P = pad64(c);
-    B200_CHECK(static_cast<size_t>(rows) * c == n_elems, "read_stage %s: expected %lld x %d elements, got %zu", name,
-               (long long)rows, c, n_elems);
+    const size_t per_clip = static_cast<size_t>(rows) * c;
+    B200_CHECK(per_clip * h->tap_clips == n_elems, "read_stage %s: expected %d x %lld x %d elements, got %zu", name,
+               h->tap_clips, (long long)rows, c, n_elems);
     B200_CUDA_OK(cudaSetDevice(h->device));
     B200_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    B200_CUDA_OK(cudaMemcpy2D(host_out, static_cast<size_t>(c) * 4, h->tap[idx].p, static_cast<size_t>(P) * 4,
-                              static_cast<size_t>(c) * 4, static_cast<size_t>(rows), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < h->tap_clips; ++b)
+        B200_CUDA_OK(cudaMemcpy2D(host_out + b * per_clip, static_cast<size_t>(c) * 4,
+                                  static_cast<const float*>(h->tap[idx].p) + static_cast<size_t>(b) * slot * P,
+                                  static_cast<size_t>(P) * 4, static_cast<size_t>(c) * 4, static_cast<size_t>(rows),
+                                  cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -811,6 +882,7 @@ int b200enc_set_stage_taps(B200Enc* h, int on) {
     if (!h->taps_on) {
         for (auto& t : h->tap) t.release();
         h->tap_samples = 0;
+        h->tap_clips = 0;
     }
     return 0;
 }
