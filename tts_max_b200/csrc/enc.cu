@@ -68,37 +68,49 @@ struct Buf {
 // ---------------------------------------------------------------------------------------------
 // conv_blocks[0]: Conv1d(1 -> 48, k = 7, padding 3), weight-normed: x0[t, c] = b[c] + sum_k w[c][k] wav[t + k - 3].
 // blockIdx.y = clip: wav is compact [clips][S], out is the slotted row space (clip b at row b * slot).
+// A thread owns 4 channels (its 28 taps and 4 biases live in registers; 128-bit stores) and walks kConv0Rows
+// consecutive samples with a sliding window of 7 input samples; P / 4 threads share a sample.
+constexpr int kConv0Rows = 32;
+
 __global__ void __launch_bounds__(256)
 enc_conv0_kernel(const float* __restrict__ wav, int S, int slot, const float* __restrict__ w /*[C][7]*/,
                  const float* __restrict__ bias, int C, int P, float* __restrict__ out /*[clips * slot][P]*/) {
     pdl_launch_dependents();
     pdl_wait();
-    // a thread owns 4 channels of one sample (128-bit stores); P / 4 threads per sample
     const int tpr = P >> 2;
     const int c0 = (threadIdx.x % tpr) * 4;
-    const int t = blockIdx.x * (blockDim.x / tpr) + threadIdx.x / tpr;
-    if (t >= S) return;
+    const int t0 = (blockIdx.x * (blockDim.x / tpr) + threadIdx.x / tpr) * kConv0Rows;
+    if (t0 >= S) return;
     wav += static_cast<size_t>(blockIdx.y) * S;
-    out += static_cast<size_t>(blockIdx.y) * slot * P;
-    float xin[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        const int i = t + k - 3;
-        xin[k] = (i >= 0 && i < S) ? __ldg(wav + i) : 0.f;
-    }
-    float acc[4];
+    out += (static_cast<size_t>(blockIdx.y) * slot + t0) * P + c0;
+    float wr[4][7], br[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int c = c0 + j;
-        float a = 0.f;
-        if (c < C) {
-            a = bias[c];
+        const bool ok = c0 + j < C;
+        br[j] = ok ? bias[c0 + j] : 0.f;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) a = fmaf(w[c * 7 + k], xin[k], a);
-        }
-        acc[j] = a;
+        for (int k = 0; k < 7; ++k) wr[j][k] = ok ? w[(c0 + j) * 7 + k] : 0.f;
     }
-    *reinterpret_cast<float4*>(out + static_cast<size_t>(t) * P + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    auto at = [&](int i) { return (i >= 0 && i < S) ? __ldg(wav + i) : 0.f; };
+    float xin[7];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xin[k + 1] = at(t0 + k - 3);
+#pragma unroll 8
+    for (int r = 0; r < kConv0Rows; ++r) {
+        if (t0 + r >= S) break;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xin[k] = xin[k + 1];
+        xin[6] = at(t0 + r + 3);
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = br[j];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) a = fmaf(wr[j][k], xin[k], a);
+            acc[j] = a;
+        }
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * P) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
 }
 
 // Activation1d(SnakeBeta) fused (activations.py:90-110, filters.py:87-135 with ratio 2, 12-tap kaiser-sinc
@@ -786,7 +798,7 @@ int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t 
 
     // ---- acoustic encoder ----
     int rows = S, slot = slot_tok * kHopTotal, c = kGenFeatures;  // valid rows per clip / rows per slot at this level
-    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 15) / 16, n_clips), dim3(256), 0, s, wav_dev, S, slot,
+    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 16 * kConv0Rows - 1) / (16 * kConv0Rows), n_clips), dim3(256), 0, s, wav_dev, S, slot,
                                (const float*)h->conv0_w, (const float*)h->conv0_b, kGenFeatures, 64, h->x[0]));
     h->launches++;
     auto take_tap = [&](int idx, int64_t slot_rows, int Pc) -> int {

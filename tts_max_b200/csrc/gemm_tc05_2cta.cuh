@@ -34,26 +34,34 @@ namespace b200 {
 
 constexpr int kGemm2Threads = 384;
 constexpr int kGemm2BlockN = 256;
-constexpr int kGemm2Stages = 5;
 constexpr int kGemm2ChunkCols = 32;  // accumulator columns per epilogue step
 
-struct Gemm2Smem {
-    static constexpr int kABytes = 128 * 128;  // this CTA's 128 rows of A, one 128-byte swizzle span
-    static constexpr int kBBytes = 128 * 128;  // this CTA's half (128 rows) of the B tile
+// Shared memory of one CTA for tiles of 256 x BLOCK_N: a stage = this CTA's 128 rows of A + its half of the B
+// tile. Narrower tiles have smaller stages, so more of them fit: 8 stages at BLOCK_N = 64 instead of 5 -- the
+// K loop of a narrow tile is bounded by TMA latency x loads in flight (encoder convs with K = 448 ... 1344,
+// B = 1 decode), not by the tensor pipe.
+template <int BLOCK_N>
+struct Gemm2SmemT {
+    static constexpr int kStages = BLOCK_N == 64 ? 8 : BLOCK_N == 128 ? 6 : 5;
+    static constexpr int kABytes = 128 * 128;            // this CTA's 128 rows of A, one 128-byte swizzle span
+    static constexpr int kBBytes = (BLOCK_N / 2) * 128;  // this CTA's half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B tiles start on 1024-byte boundaries");
     // per epilogue warp: one 32-row x 32-column fp32 staging box (128-byte rows, SWIZZLE_128B)
     // and two 16-bit boxes (64-byte rows, SWIZZLE_64B). A TMA store has read its box well within
     // one chunk period (measured), so the fp32 box is not double-buffered.
     static constexpr int kBox32Bytes = 32 * kGemm2ChunkCols * 4;
     static constexpr int kBox16Bytes = 32 * kGemm2ChunkCols * 2;
     static constexpr int kEpiWarpBytes = kBox32Bytes + 2 * kBox16Bytes;
-    static constexpr int kEpiOffset = kGemm2Stages * kStageBytes;
+    static constexpr int kEpiOffset = kStages * kStageBytes;
     static constexpr int kBarOffset = kEpiOffset + 8 * kEpiWarpBytes;
     // full[stages], empty[stages], tmem_full[2], tmem_empty[2]
-    static constexpr int kNumBars = 2 * kGemm2Stages + 4;
+    static constexpr int kNumBars = 2 * kStages + 4;
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
+    static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
-static_assert(Gemm2Smem::kTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+using Gemm2Smem = Gemm2SmemT<256>;
+constexpr int kGemm2Stages = Gemm2Smem::kStages;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -206,13 +214,13 @@ template <typename InT, bool kGnStats, int BLOCK_N, bool kChain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc05_2cta_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams cp) {
     const GemmParams& p = cp.g[0];  // plain GEMM: the only one; chains: per-tile parameters are cp.g[g]
-    using SM = Gemm2Smem;
+    using SM = Gemm2SmemT<BLOCK_N>;
     static_assert(BLOCK_N == 256 || BLOCK_N == 192 || BLOCK_N == 128 || BLOCK_N == 64, "tile width");
     constexpr int kHalfN = BLOCK_N / 2;  // B rows staged by each CTA = accumulator columns per epilogue warp
     constexpr uint32_t kStageTx = 2 * (SM::kABytes + kHalfN * 128);  // bytes both CTAs land per stage
     constexpr int BLOCK_K = 64;
     constexpr int UMMA_K = 16;
-    constexpr int kStages = kGemm2Stages;
+    constexpr int kStages = SM::kStages;
     // two accumulator stages of BLOCK_N fp32 columns; allocations are powers of two (2 x 192 -> 512)
     constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 128 ? 128 : 2 * BLOCK_N <= 256 ? 256 : 512;
     static_assert(sizeof(InT) == 2, "2-CTA kernel is instantiated for bf16 / fp16 operands");
@@ -684,12 +692,12 @@ int launch_gemm_tc05_2cta(const ChainMaps& maps, const ChainParams& cp, cudaStre
     static PerDeviceOnce once;
     if (once.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Gemm2Smem::kTotal));
+                                          Gemm2SmemT<BLOCK_N>::kTotal));
     }
     int clusters = cp.tile_end[cp.n_gemm - 1];
     if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
     if (clusters < 1) return 0;
-    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2Smem::kTotal, stream, maps, cp));
+    B200_CUDA_OK(launch_kernel(kern, dim3(2 * clusters), dim3(kGemm2Threads), Gemm2SmemT<BLOCK_N>::kTotal, stream, maps, cp));
     return 0;
 }
 
