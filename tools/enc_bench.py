@@ -1,9 +1,9 @@
 """Encode-direction throughput: AcousticEncoder + SemanticEncoder + fusion + quantise on one B200.
 
-    python tools/enc_bench.py [--clips 16] [--seconds 10] [--steps 10] [--cpu]
+    python tools/enc_bench.py [--clips 16] [--seconds 10] [--steps 10] [--group G] [--cpu]
 
 Prints one JSON line: audio-s/s device-timed (CUDA events around `steps` passes over the batch, inputs resident),
-launches per utterance, and -- with --cpu -- the oracle port of the reference modules on the host cores for one
+launches per pass (80 per launch sequence; --group: clips per launch sequence), and -- with --cpu -- the oracle port of the reference modules on the host cores for one
 clip. The w2v-BERT hidden state is a synthetic input (that model stays in HuggingFace).
 """
 import argparse
