@@ -140,6 +140,63 @@ def synthetic_ids(n_utts: int, tokens: int, seed: int):
     return torch.randint(0, 65536, (n_utts * tokens,), generator=g, dtype=torch.int64)
 
 
+def measure_encode(dev, precision: str):
+    """Encode direction on this GPU: 16 clips x 10 s through Encoder.forward (acoustic + semantic
+    encoders, fusion, quantise; the w2v-BERT hidden state is a synthetic input), device-timed. Random weights with
+    the shapes of the reference state dict (weight-normed convs with g = 0.4 |v|, alpha = beta = 0, 12-tap
+    windowed-sinc filters): throughput does not depend on the values."""
+    import math
+    import torch
+    from tts_max_b200.codec import encoder
+    g = torch.Generator().manual_seed(11)
+    n = torch.arange(12, dtype=torch.float32) - 5.5
+    lp = torch.sinc(n / 2) * torch.hann_window(12, periodic=False)
+    lp = (lp / lp.sum()).view(1, 1, 12)
+    sd = {}
+    shapes = encoder.expected_state_dict_shapes()
+    for key, shape in shapes.items():
+        if key.endswith("filter"):
+            sd[key] = lp.clone()
+        elif key.endswith(("alpha", "beta")):
+            sd[key] = torch.zeros(shape)
+        elif key.endswith("weight_g"):
+            continue
+        else:
+            fan_in = math.prod(shape[1:]) if len(shape) > 1 else shape[0]
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(max(fan_in, 1))
+    for key, shape in shapes.items():
+        if key.endswith("weight_g"):
+            v = sd[key[:-1] + "v"]
+            sd[key] = 0.4 * v.flatten(1).norm(dim=1).view(shape)
+    enc = encoder.Encoder(pre_bound=False, precision=precision)
+    enc.load_state_dict(sd)
+    enc.to(dev).eval()
+    clips, S = 16, 160000
+    wav = (0.3 * torch.randn(clips, 1, S, generator=g)).to(dev)
+    w2v = torch.randn(clips, S // 320, 1024, generator=g).to(dev)
+    for _ in range(2):
+        ids = enc(wav, w2v)
+    torch.cuda.synchronize(dev)
+    n0 = enc.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    e0.record()
+    for _ in range(steps):
+        ids = enc(wav, w2v)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    assert ids.shape == (clips, 1, S // 320) and int(ids.min()) >= 0 and int(ids.max()) < 65536
+    launches = (enc.launch_count() - n0) // steps
+    del enc
+    torch.cuda.empty_cache()
+    return {"value": round(clips * S / 16000 / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3),
+            "gpu_launches_per_step": int(launches),
+            "workload": "16 clips x 10 s of 16 kHz audio -> 16 x 500 ids in one launch sequence (Encoder.forward: acoustic + "
+                        "semantic encoders, fusion, quantise; synthetic w2v-BERT hidden state, random weights)",
+            "timing": "CUDA events around 5 back-to-back passes, inputs resident"}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle (CPU restatement of the reference algorithm)
 # ------------------------------------------------------------------------------------------------
@@ -629,6 +686,10 @@ def run_ours(args):
                    "c1_4x250": {"ms_per_step": round(c1_ms, 4), "value": round(20.0 / (c1_ms / 1e3), 1), "unit": UNIT,
                                 "timing": "CUDA events around 50 back-to-back steps, L2-warm"}}
 
+    encode = None
+    if rank == 0 and world == 1 and not args.no_encode and args.model == "xcodec2":
+        encode = measure_encode(dev, args.precision)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "xcodec2":
         # the reference algorithm on this box's host cores, at N = 1 only (at N > 1 the other ranks would
         # spin at a barrier on the cores the CPU decode needs)
@@ -663,6 +724,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "c3_strong": c3,
             "latency": latency,
+            "encode": encode,
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms_in_step.items()},
             "stage_ms_event_fenced": {k: round(v, 4) for k, v in stage_ms.items()},
             "wall_s_timed_region": round(t_wall, 4),
@@ -688,6 +750,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the config-3 strong-scaling block")
     ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 / config-1 latency block")
+    ap.add_argument("--no-encode", action="store_true", help="skip the encode-direction block (SURVEY 8f-3)")
     ap.add_argument("--no-early-weights", action="store_true", help="A/B: GEMM weight loads only after griddepcontrol.wait")
     ap.add_argument("--chain", action="store_true", help="A/B: per-block GEMM chains (one persistent launch for c_proj -> fc1 -> fc2 -> next c_attn)")
     ap.add_argument("--istft-tile", type=int, default=0, help="A/B: output hops per ISTFT CTA (12 or 28)")

@@ -482,9 +482,9 @@ int snake_launch(B200Enc* h, const float* x, int T, int slot, int clips, int P, 
 }
 
 int snake(B200Enc* h, const float* x, int T, int slot, int clips, int P, const ActW& w, void* out, cudaStream_t s) {
-    // 67-row chunks (8 % warm-up overhead) once they still give every SM ~two full sets of warps, else 19-row chunks
+    // 67-row chunks (8 % warm-up overhead) once they still give every SM a full set of warps, else 19-row chunks
     const int64_t warps67 = static_cast<int64_t>((slot + 66) / 67) * (P / 64) * clips;
-    if (warps67 >= 2 * 64 * kNumSMs) return snake_launch<12>(h, x, T, slot, clips, P, w, out, s);
+    if (warps67 >= 64 * kNumSMs) return snake_launch<12>(h, x, T, slot, clips, P, w, out, s);
     return snake_launch<4>(h, x, T, slot, clips, P, w, out, s);
 }
 
