@@ -18,7 +18,8 @@ COLS = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "LDTM", "STTM", "HMMA", "MUFU
 FULL = {"gemm_tc05_2cta_kernel<__nv_bfloat16, false, 256, false>": "gemm_tc05_2cta_bf16_n256",
         "attention_tc05_kernel<__nv_bfloat16>": "attention_tc05_bf16",
         "istft_kernel<320, 16>": "istft_hop320_16warps",
-        "snake_aa_kernel<__nv_bfloat16>": "snake_aa_bf16"}
+        "snake_aa_kernel<__nv_bfloat16, 12>": "snake_aa_bf16_67rows",
+        "gemm_tc05_2cta_kernel<__nv_bfloat16, false, 192, false>": "gemm_tc05_2cta_bf16_n192"}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--tag", default="r02")
