@@ -268,9 +268,10 @@ int b200codec_istft(B200Codec* h, const float* x_pred_dev, int ld, const int32_t
                     int n_utts, float* wav_dev, void* stream);
 
 /* Generic tensor-core GEMM / implicit conv1d used by every dense layer of the path
- * (see csrc/gemm_tc05.cuh). a: [M, Cin] operand dtype (per `precision`), w: [N, taps*Cin]
- * same dtype, out: [M, ldc] (out_dtype: 0 = fp32, 1 = operand dtype).
- * out = act(conv(a, w) + bias) + residual. */
+ * (see csrc/gemm_tc05.cuh, gemm_tc05_2cta.cuh). a: [M, Cin] operand dtype (per `precision`), Cin a
+ * multiple of 64; w: [N, taps*Cin] same dtype; out: [M, ldc] (out_dtype: 0 = fp32, 1 = operand dtype),
+ * ldc >= N rounded up to 64 (columns [N, ldc) of that range are written as the product with zero weights);
+ * bias / residual need N % 64 == 0. out = act(conv(a, w) + bias) + residual. */
 int b200codec_gemm(int precision, const void* a_dev, const void* w_dev, int M, int N, int Cin,
                    int taps, void* out_dev, int out_dtype, int ldc, const float* bias_dev,
                    const float* residual_dev, int ld_res, int act, void* stream);

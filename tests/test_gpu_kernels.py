@@ -27,8 +27,8 @@ def gemm(prec, a, w, taps=1, out_fp32=True, bias=None, residual=None, act=0, ldc
     code, dt = PREC[prec]
     M, Cin = a.shape
     N = w.shape[0]
-    n32 = (N + 31) // 32 * 32
-    ldc = ldc or n32
+    n64 = (N + 63) // 64 * 64   # tiles are 64 columns wide at least; ragged N: weight rows past N read as zeros
+    ldc = ldc or n64
     out = torch.full((M, ldc), float("nan"), device="cuda", dtype=torch.float32 if out_fp32 else dt)
     _lib.check(_lib.load().b200codec_gemm(code, ptr(a), ptr(w), M, N, Cin, taps, ptr(out), 0 if out_fp32 else 1,
                                           ldc, ptr(bias), ptr(residual), residual.shape[1] if residual is not None else 0,

@@ -1900,13 +1900,15 @@ int b200codec_gemm(int precision, const void* a_dev, const void* w_dev, int M, i
     c.out = out_dev;
     c.out_fp32 = out_dtype == 0 ? 1 : 0;
     c.ldc = ldc;
-    c.n_store = (N + 31) / 32 * 32;
+    c.n_store = (N + 63) / 64 * 64;  // weight rows past N read as zeros (TMA out-of-bounds fill)
     c.bias = bias_dev;
     c.residual = residual_dev;
     c.ld_res = ld_res;
     c.row_valid = nullptr;
     c.act = act;
-    B200_CHECK(c.n_store <= ldc, "gemm: ldc (%d) must cover N rounded up to 32 (%d)", ldc, c.n_store);
+    B200_CHECK(c.n_store <= ldc, "gemm: ldc (%d) must cover N rounded up to 64 (%d)", ldc, c.n_store);
+    B200_CHECK(N % 64 == 0 || (bias_dev == nullptr && residual_dev == nullptr),
+               "gemm: bias / residual need N (%d) to be a multiple of 64", N);
     return launch_gemm(c, static_cast<cudaStream_t>(stream));
 }
 

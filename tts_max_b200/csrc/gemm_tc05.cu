@@ -111,17 +111,6 @@ __global__ void repack_convT_phase_kernel(const float* __restrict__ v, const flo
     }
 }
 
-template <typename InT>
-int dispatch(const GemmCall& c, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-             bool wide, cudaStream_t stream) {
-    if (c.out_fp32) {
-        if (wide) return launch_gemm_tc05<256, InT, float, 4>(ta, tb, p, stream);
-        return launch_gemm_tc05<128, InT, float, 6>(ta, tb, p, stream);
-    }
-    if (wide) return launch_gemm_tc05<256, InT, InT, 4>(ta, tb, p, stream);
-    return launch_gemm_tc05<128, InT, InT, 6>(ta, tb, p, stream);
-}
-
 }  // namespace
 
 namespace {
@@ -199,41 +188,10 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
     return make_tmap_box(map, base, dtype, rows, cols, ld_elems, 128 / esz, box_rows);
 }
 
-// kernel selection: CTA pairs (256x256 per cluster) whenever N tiles evenly -- for every M, so
-// an utterance sees the same arithmetic alone or inside a batch; the 1-CTA kernel covers the
-// ragged head GEMM (N = 1282).
-enum GemmKind { kGemm1CtaN128 = 0, kGemm1CtaN256 = 1, kGemm2Cta = 2 };
-static GemmKind gemm_kind(const GemmCall& c) {
-    const bool n256 = c.n_store >= 256 && (c.n_store % 256 == 0);
-    if (n256) return kGemm2Cta;
-    // N a multiple of 64 but not of 256 (the encoder's 64 ... 384-channel convs): the CTA-pair kernel's 256 x 64
-    // tiles. Its TMA-store epilogue drains a tile several times faster than the 1-CTA kernel's row-per-lane
-    // stores, and these GEMMs (K = 64 ... 1344, 10^5 rows) are epilogue-bound
-    if (c.n_store >= 64 && c.n_store % 64 == 0) return kGemm2Cta;
-    if (n256 && c.n_store >= 1024) return kGemm1CtaN256;
-    return kGemm1CtaN128;
-}
-static bool gemm_is_wide(const GemmCall& c) { return gemm_kind(c) == kGemm1CtaN256; }
-bool gemm_uses_cta_pairs(int a_rows, int n_store) {
-    GemmCall c{};
-    c.a_rows = a_rows;
-    c.n_store = n_store;
-    return gemm_kind(c) == kGemm2Cta;
-}
-
-int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out) {
-    const int dt = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
-    if (tmap_a_out != nullptr &&
-        make_tmap_2d(static_cast<CUtensorMap*>(tmap_a_out), c.a, dt, c.a_rows, c.Cin, c.Cin,
-                     kGemmBlockM))
-        return 1;
-    if (tmap_b_out != nullptr &&
-        make_tmap_2d(static_cast<CUtensorMap*>(tmap_b_out), c.w, dt, c.N,
-                     static_cast<uint64_t>(c.taps) * c.Cin, static_cast<uint64_t>(c.taps) * c.Cin,
-                     gemm_is_wide(c) ? 256 : 128))
-        return 1;
-    return 0;
-}
+// Every GEMM runs on the CTA-pair kernel; N must tile by 64 (the callers pad: head.out 1282 -> 1536, the
+// encoder's 48 / 96 channels -> 64 / 128). For every M, so an utterance sees the same arithmetic alone or
+// inside a batch.
+bool gemm_uses_cta_pairs(int /*a_rows*/, int n_store) { return n_store >= 64 && n_store % 64 == 0; }
 
 #ifdef B200_GEMM_TRACE
 unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
@@ -280,20 +238,16 @@ int fill_params(const GemmCall& c, GemmParams* out) {
 #ifdef B200_GEMM_TRACE
     p.trace = g_gemm_trace;
 #endif
-    const bool fused = c.ss_in != nullptr || c.out16 != nullptr || c.ss_out != nullptr;
-    B200_CHECK(!fused || gemm_kind(c) == kGemm2Cta,
-               "gemm: the RMSNorm-fused epilogue needs the CTA-pair kernel (N %% 256 == 0)");
+    B200_CHECK(c.n_store >= 64 && c.n_store % 64 == 0, "gemm: N (%d stored columns) must be a multiple of 64", c.n_store);
     B200_CHECK(c.out16 == nullptr || c.out_fp32, "gemm: out16 requires fp32 output");
     B200_CHECK(c.ss_out == nullptr || (c.out_fp32 && c.n_store == 1024),
                "gemm: ss_out requires fp32 output with N == 1024");
-    B200_CHECK(c.residual == nullptr || gemm_kind(c) != kGemm2Cta ||
-                   ((reinterpret_cast<uintptr_t>(c.residual) & 31) == 0 && c.ld_res % 8 == 0),
+    B200_CHECK(c.residual == nullptr || ((reinterpret_cast<uintptr_t>(c.residual) & 31) == 0 && c.ld_res % 8 == 0),
                "gemm: the residual must be 32-byte aligned with a row pitch that is a multiple of 8");
     p.gn_stats = c.gn_stats;
     p.gn_row_utt = c.gn_row_utt;
-    B200_CHECK(c.gn_stats == nullptr ||
-                   (gemm_kind(c) == kGemm2Cta && c.out_fp32 && c.n_store == 1024 && c.gn_row_utt != nullptr),
-               "gemm: GroupNorm statistics need the CTA-pair kernel, fp32 output, N == 1024 and a row -> utterance map");
+    B200_CHECK(c.gn_stats == nullptr || (c.out_fp32 && c.n_store == 1024 && c.gn_row_utt != nullptr),
+               "gemm: GroupNorm statistics need fp32 output, N == 1024 and a row -> utterance map");
     p.has32 = c.out_fp32 ? 1 : 0;
     p.has16 = (!c.out_fp32 || c.out16 != nullptr) ? 1 : 0;
     *out = p;
@@ -393,30 +347,21 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     GemmParams p;
     if (fill_params(c, &p)) return 1;
     if (c.a_rows <= 0) return 0;
-    if (gemm_kind(c) == kGemm2Cta) {
-        int block_n = 256;
-        if (c.n_store % 256 != 0) block_n = g_gemm_narrow_tiles == 2 ? 64 : pick_block_n(c);
-        else if (c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store)) block_n = 64;
-        alignas(64) ChainMaps maps;
-        ChainParams cp{};
-        if (fill_maps_2cta(c, block_n, &maps.a[0], &maps.b[0], &maps.o32[0], &maps.o16[0])) return 1;
-        cp.n_gemm = 1;
-        cp.num_m = (c.a_rows + 255) / 256;
-        cp.num_n[0] = c.n_store / block_n;
-        cp.tile_end[0] = cp.num_m * cp.num_n[0];
-        cp.full[0] = 0;
-        cp.counters = nullptr;
-        cp.early_weights = g_gemm_early_weights;
-        cp.g[0] = p;
-        return launch_2cta<false>(c.precision, p.gn_stats != nullptr, block_n, maps, cp, stream);
-    }
-    const bool wide = gemm_is_wide(c);
-    alignas(64) CUtensorMap ta, tb;
-    if (c.tmap_a != nullptr) ta = *static_cast<const CUtensorMap*>(c.tmap_a);
-    if (c.tmap_b != nullptr) tb = *static_cast<const CUtensorMap*>(c.tmap_b);
-    if (encode_gemm_tmaps(c, c.tmap_a ? nullptr : &ta, c.tmap_b ? nullptr : &tb)) return 1;
-    if (c.precision == kPrecBf16) return dispatch<__nv_bfloat16>(c, ta, tb, p, wide, stream);
-    return dispatch<__half>(c, ta, tb, p, wide, stream);
+    int block_n = 256;
+    if (c.n_store % 256 != 0) block_n = g_gemm_narrow_tiles == 2 ? 64 : pick_block_n(c);
+    else if (c.tmap_b == nullptr && want_narrow(c.a_rows, c.n_store)) block_n = 64;
+    alignas(64) ChainMaps maps;
+    ChainParams cp{};
+    if (fill_maps_2cta(c, block_n, &maps.a[0], &maps.b[0], &maps.o32[0], &maps.o16[0])) return 1;
+    cp.n_gemm = 1;
+    cp.num_m = (c.a_rows + 255) / 256;
+    cp.num_n[0] = c.n_store / block_n;
+    cp.tile_end[0] = cp.num_m * cp.num_n[0];
+    cp.full[0] = 0;
+    cp.counters = nullptr;
+    cp.early_weights = g_gemm_early_weights;
+    cp.g[0] = p;
+    return launch_2cta<false>(c.precision, p.gn_stats != nullptr, block_n, maps, cp, stream);
 }
 
 namespace {
@@ -487,7 +432,7 @@ bool gemm_chain_supported(const GemmCall* calls, int n) {
     if (n < 2 || n > kChainMax) return false;
     for (int i = 0; i < n; ++i) {
         const GemmCall& c = calls[i];
-        if (gemm_kind(c) != kGemm2Cta || c.taps != 1 || c.gn_stats != nullptr || c.a_rows != calls[0].a_rows ||
+        if (c.n_store % 256 != 0 || c.taps != 1 || c.gn_stats != nullptr || c.a_rows != calls[0].a_rows ||
             c.precision != calls[0].precision || c.row_valid != nullptr)
             return false;
     }

@@ -149,10 +149,8 @@ int launch_gemm(const GemmCall& c, cudaStream_t stream);
 // `counters` = n * ceil(rows / 256) uint32, zero on entry (see gemm_tc05_2cta.cuh).
 bool gemm_chain_supported(const GemmCall* calls, int n);
 int launch_gemm_chain(const GemmCall* calls, int n, uint32_t* counters, cudaStream_t stream);
-// true when launch_gemm would pick the CTA-pair kernel (the only one with the fused-norm epilogue)
+// true when launch_gemm accepts the shape (N a multiple of 64; the fused-norm epilogue is always available)
 bool gemm_uses_cta_pairs(int a_rows, int n_store);
-// encode the descriptors launch_gemm would build for `c` into tmap_a_out / tmap_b_out
-int encode_gemm_tmaps(const GemmCall& c, void* tmap_a_out, void* tmap_b_out);
 
 // ---- weight repack helpers (codec.cu uses them at finalize) ----
 // dst[n, tap*Cin + c] = src[n, c, tap]  (src is torch Conv1d weight [Cout, Cin, taps]), cast
