@@ -9,8 +9,10 @@
 //   SemanticEncoder.forward        tts/core/codec/encoder_modules.py:72-125
 //   fusion_layer, Encoder.quantize tts/core/codec/encoder.py:42, 66-78
 //
-// B200 mapping. Activations are token-major (channels-last) [rows, C] like the decoder's, C padded to a multiple
-// of 64 (48 -> 64, 96 -> 128; pad channels stay exactly zero), one utterance per launch sequence:
+// B200 mapping. Activations are token-major (channels-last) [rows, C] like the decoder's, dense (row pitch C, also
+// for C = 48 and 96: the GEMM tiles are 64 wide, TMA out-of-bounds fill pads the operand rows with zeros in shared
+// memory and the TMA stores drop the pad columns, so the padding costs FLOPs but no memory traffic), the clips of a
+// call in one launch sequence:
 //   * every Conv1d is the tcgen05 GEMM of gemm_tc05*.cuh: k = 7 dilated = 7 row-shifted K-slabs with a row
 //     stride of `dilation` (zero padding = TMA out-of-bounds fill at the array ends); the strided
 //     down-sampling conv (k = 2s, stride s) is a 3-tap conv over the SAME buffer viewed as [rows / s, s * C]
@@ -69,27 +71,27 @@ struct Buf {
 // conv_blocks[0]: Conv1d(1 -> 48, k = 7, padding 3), weight-normed: x0[t, c] = b[c] + sum_k w[c][k] wav[t + k - 3].
 // blockIdx.y = clip: wav is compact [clips][S], out is the slotted row space (clip b at row b * slot).
 // A thread owns 4 channels (its 28 taps and 4 biases live in registers; 128-bit stores) and walks kConv0Rows
-// consecutive samples with a sliding window of 7 input samples; P / 4 threads share a sample.
+// consecutive samples with a sliding window of 7 input samples; C / 4 threads share a sample; out rows are dense.
 constexpr int kConv0Rows = 32;
 
 __global__ void __launch_bounds__(256)
 enc_conv0_kernel(const float* __restrict__ wav, int S, int slot, const float* __restrict__ w /*[C][7]*/,
-                 const float* __restrict__ bias, int C, int P, float* __restrict__ out /*[clips * slot][P]*/) {
+                 const float* __restrict__ bias, int C, float* __restrict__ out /*[clips * slot][C]*/) {
     pdl_launch_dependents();
     pdl_wait();
-    const int tpr = P >> 2;
-    const int c0 = (threadIdx.x % tpr) * 4;
-    const int t0 = (blockIdx.x * (blockDim.x / tpr) + threadIdx.x / tpr) * kConv0Rows;
+    const int quads = C >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c0 = (idx % quads) * 4;
+    const int t0 = (idx / quads) * kConv0Rows;
     if (t0 >= S) return;
     wav += static_cast<size_t>(blockIdx.y) * S;
-    out += (static_cast<size_t>(blockIdx.y) * slot + t0) * P + c0;
+    out += (static_cast<size_t>(blockIdx.y) * slot + t0) * C + c0;
     float wr[4][7], br[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const bool ok = c0 + j < C;
-        br[j] = ok ? bias[c0 + j] : 0.f;
+        br[j] = bias[c0 + j];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) wr[j][k] = ok ? w[(c0 + j) * 7 + k] : 0.f;
+        for (int k = 0; k < 7; ++k) wr[j][k] = w[(c0 + j) * 7 + k];
     }
     auto at = [&](int i) { return (i >= 0 && i < S) ? __ldg(wav + i) : 0.f; };
     float xin[7];
@@ -109,7 +111,7 @@ enc_conv0_kernel(const float* __restrict__ wav, int S, int slot, const float* __
             for (int k = 0; k < 7; ++k) a = fmaf(wr[j][k], xin[k], a);
             acc[j] = a;
         }
-        *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * P) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * C) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
 }
 
@@ -226,11 +228,12 @@ snake_aa_kernel(const float* __restrict__ x, int T, int slot, int P, const float
     pdl_launch_dependents();
     pdl_wait();
     constexpr int K = kM * 6 - 5;  // rows per chunk
-    // warp = (chunk of K rows, group of 64 channels); lane = channel pair
-    const int cgroups = P >> 6;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int chunk = w / cgroups;
-    const int c = (w - chunk * cgroups) * 64 + (threadIdx.x & 31) * 2;
+    // thread = (chunk of K rows, channel pair), pairs fastest: for P a multiple of 64 a warp is 64 channels of one
+    // chunk; for P = 48 / 96 a warp may straddle two chunks (two coalesced segments per access)
+    const int pairs = P >> 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = idx / pairs;
+    const int c = (idx - chunk * pairs) * 2;
     const int t0 = chunk * K;
     if (t0 >= slot) return;
     x += static_cast<size_t>(blockIdx.y) * slot * P;
@@ -282,23 +285,23 @@ __global__ void enc_repack_conv_kernel(const float* __restrict__ v, const float*
     }
 }
 
-// strided conv (k = 2s, stride s, padding p) as a 3-tap conv over super-rows of s input rows:
-// dst[n][(tap' * s + r) * Cinpad + c] = w[n][c][s (tap' - 1) + r + p] when that kernel index exists, else 0
+// strided conv (k = 2s, stride s, padding p) as a 3-tap conv over super-rows of s input rows (s * Cin dense columns,
+// padded as a whole to Kt = a multiple of 64):
+// dst[n][tap' * Kt + r * Cin + c] = w[n][c][s (tap' - 1) + r + p] when that kernel index exists, else 0
 template <typename T>
 __global__ void enc_repack_strided_kernel(const float* __restrict__ v, const float* __restrict__ scale, T* __restrict__ dst,
-                                          int Cout, int Cin, int s, int p, int Npad, int Cinpad) {
+                                          int Cout, int Cin, int s, int p, int Npad, int Kt) {
     const int k = 2 * s;
-    const size_t total = static_cast<size_t>(Npad) * 3 * s * Cinpad;
+    const size_t total = static_cast<size_t>(Npad) * 3 * Kt;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % Cinpad);
-        size_t rest = i / Cinpad;
-        const int r = static_cast<int>(rest % s);
-        rest /= s;
+        const int col = static_cast<int>(i % Kt);
+        const size_t rest = i / Kt;
         const int tp = static_cast<int>(rest % 3);
         const int n = static_cast<int>(rest / 3);
+        const int r = col / Cin, c = col - r * Cin;
         const int kk = s * (tp - 1) + r + p;
         float w = 0.f;
-        if (n < Cout && c < Cin && kk >= 0 && kk < k) w = v[(static_cast<size_t>(n) * Cin + c) * k + kk] * scale[n];
+        if (n < Cout && r < s && kk >= 0 && kk < k) w = v[(static_cast<size_t>(n) * Cin + c) * k + kk] * scale[n];
         dst[i] = Half16<T>::from_float(w);
     }
 }
@@ -458,11 +461,11 @@ int repack_conv(const float* v, const float* scale, void* dst, int Cout, int Cin
     return 0;
 }
 template <typename T>
-int repack_strided(const float* v, const float* scale, void* dst, int Cout, int Cin, int st, int p, int Npad, int Cinpad,
+int repack_strided(const float* v, const float* scale, void* dst, int Cout, int Cin, int st, int p, int Npad, int Kt,
                    cudaStream_t s) {
-    const size_t total = static_cast<size_t>(Npad) * 3 * st * Cinpad;
+    const size_t total = static_cast<size_t>(Npad) * 3 * Kt;
     const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, 8192));
-    enc_repack_strided_kernel<T><<<grid, 256, 0, s>>>(v, scale, static_cast<T*>(dst), Cout, Cin, st, p, Npad, Cinpad);
+    enc_repack_strided_kernel<T><<<grid, 256, 0, s>>>(v, scale, static_cast<T*>(dst), Cout, Cin, st, p, Npad, Kt);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -470,8 +473,8 @@ int repack_strided(const float* v, const float* scale, void* dst, int Cout, int 
 template <int kM>
 int snake_launch(B200Enc* h, const float* x, int T, int slot, int clips, int P, const ActW& w, void* out, cudaStream_t s) {
     constexpr int K = kM * 6 - 5;
-    const int warps = ((slot + K - 1) / K) * (P / 64);
-    dim3 grid((warps + 7) / 8, clips);
+    const int64_t threads = static_cast<int64_t>((slot + K - 1) / K) * (P / 2);
+    dim3 grid(static_cast<unsigned>((threads + 255) / 256), clips);
     if (h->precision == kPrecBf16)
         B200_CUDA_OK(launch_kernel(snake_aa_kernel<__nv_bfloat16, kM>, grid, dim3(256), 0, s, x, T, slot, P, w.alpha, w.inv_beta, w.f,
                                    static_cast<__nv_bfloat16*>(out)));
@@ -483,30 +486,34 @@ int snake_launch(B200Enc* h, const float* x, int T, int slot, int clips, int P, 
 
 int snake(B200Enc* h, const float* x, int T, int slot, int clips, int P, const ActW& w, void* out, cudaStream_t s) {
     // 67-row chunks (8 % warm-up overhead) once they still give every SM a full set of warps, else 19-row chunks
-    const int64_t warps67 = static_cast<int64_t>((slot + 66) / 67) * (P / 64) * clips;
+    const int64_t warps67 = static_cast<int64_t>((slot + 66) / 67) * (P / 2) * clips / 32;
     if (warps67 >= 64 * kNumSMs) return snake_launch<12>(h, x, T, slot, clips, P, w, out, s);
     return snake_launch<4>(h, x, T, slot, clips, P, w, out, s);
 }
 
-GemmCall conv_call(B200Enc* h, const void* a, int rows, int Cin, const ConvW& w, int N, int taps, int dil, void* out,
-                   bool out_fp32, int ldc, const float* residual, int act, const uint8_t* row_valid = nullptr) {
+// Conv / Linear over dense [rows, a_cols] -> [rows, out_cols] matrices; the GEMM sees them padded to multiples of 64
+// (weights and biases are laid out padded at load time)
+GemmCall conv_call(B200Enc* h, const void* a, int rows, int a_cols, const ConvW& w, int out_cols, int taps, int dil, void* out,
+                   bool out_fp32, const float* residual, int act, const uint8_t* row_valid = nullptr) {
     GemmCall c{};
     c.precision = h->precision;
     c.a = a;
     c.a_rows = rows;
-    c.Cin = Cin;
+    c.Cin = pad64(a_cols);
+    c.a_cols = a_cols % 64 ? a_cols : 0;
     c.w = w.w;
-    c.N = N;
+    c.N = pad64(out_cols);
     c.taps = taps;
     c.tap_pad = -1;
     c.tap_dil = dil;
     c.out = out;
     c.out_fp32 = out_fp32 ? 1 : 0;
-    c.ldc = ldc;
-    c.n_store = N;
+    c.ldc = out_cols;
+    c.n_store = c.N;
+    c.out_cols = out_cols % 64 ? out_cols : 0;
     c.bias = w.bias;
     c.residual = residual;
-    c.ld_res = ldc;
+    c.ld_res = out_cols;
     c.row_valid = row_valid;
     c.act = act;
     c.out16_scale = 1.f;
@@ -531,7 +538,7 @@ int ensure_ws(B200Enc* h, int64_t S) {  // S: slotted samples of the whole batch
     int c = kGenFeatures;
     size_t off_x[kStages + 1], off_h[kStages], off_a[kStages + 1];
     for (int i = 0; i <= kStages; ++i) {
-        const size_t P = pad64(c);
+        const size_t P = c;  // dense rows
         off_x[i] = total; total += al(static_cast<size_t>(rows) * P * 4);
         if (i < kStages) { off_h[i] = total; total += al(static_cast<size_t>(rows) * P * 4); }
         off_a[i] = total; total += al(static_cast<size_t>(rows) * P * es);
@@ -726,6 +733,7 @@ int b200enc_finalize_weights(B200Enc* h, void* stream) {
         B200_CUDA_OK(cudaMemcpyAsync(h->conv0_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice, s));
         B200_CUDA_OK(cudaStreamSynchronize(s));
         h->conv0_b = padvec(h->m(a + "conv_blocks.0.bias"), kGenFeatures, 64, 0);
+        static_assert(kGenFeatures % 4 == 0, "enc_conv0_kernel owns channel quads");
     }
     int c = kGenFeatures;
     for (int i = 0; i < kStages; ++i) {
@@ -740,13 +748,13 @@ int b200enc_finalize_weights(B200Enc* h, void* stream) {
         }
         if (make_act(p + "block.3.", c, &st.act)) return 1;
         {
-            const int sdn = kStrides[i], Np = pad64(2 * c), Cp = pad64(c);
+            const int sdn = kStrides[i], Np = pad64(2 * c), Kt = pad64(sdn * c);
             const std::string q = p + "block.4.";
             if (launch_weightnorm_scale(h->m(q + "weight_g"), h->m(q + "weight_v"), 2 * c, c * 2 * sdn, scale, s)) return 1;
-            st.down.w = takew(static_cast<size_t>(Np) * 3 * sdn * Cp);
+            st.down.w = takew(static_cast<size_t>(Np) * 3 * Kt);
             const int pd = sdn / 2 + sdn % 2;
-            if (bf ? repack_strided<__nv_bfloat16>(h->m(q + "weight_v"), scale, st.down.w, 2 * c, c, sdn, pd, Np, Cp, s)
-                   : repack_strided<__half>(h->m(q + "weight_v"), scale, st.down.w, 2 * c, c, sdn, pd, Np, Cp, s))
+            if (bf ? repack_strided<__nv_bfloat16>(h->m(q + "weight_v"), scale, st.down.w, 2 * c, c, sdn, pd, Np, Kt, s)
+                   : repack_strided<__half>(h->m(q + "weight_v"), scale, st.down.w, 2 * c, c, sdn, pd, Np, Kt, s))
                 return 1;
             st.down.bias = padvec(h->m(q + "bias"), 2 * c, Np, 0);
         }
@@ -798,8 +806,11 @@ int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t 
 
     // ---- acoustic encoder ----
     int rows = S, slot = slot_tok * kHopTotal, c = kGenFeatures;  // valid rows per clip / rows per slot at this level
-    B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((S + 16 * kConv0Rows - 1) / (16 * kConv0Rows), n_clips), dim3(256), 0, s, wav_dev, S, slot,
-                               (const float*)h->conv0_w, (const float*)h->conv0_b, kGenFeatures, 64, h->x[0]));
+    {
+        const int threads = ((S + kConv0Rows - 1) / kConv0Rows) * (kGenFeatures / 4);
+        B200_CUDA_OK(launch_kernel(enc_conv0_kernel, dim3((threads + 255) / 256, n_clips), dim3(256), 0, s, wav_dev, S, slot,
+                                   (const float*)h->conv0_w, (const float*)h->conv0_b, kGenFeatures, h->x[0]));
+    }
     h->launches++;
     auto take_tap = [&](int idx, int64_t slot_rows, int Pc) -> int {
         if (!h->taps_on) return 0;
@@ -810,21 +821,21 @@ int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t 
         h->tap_clips = n_clips;
         return 0;
     };
-    if (take_tap(0, slot, 64)) return 1;
+    if (take_tap(0, slot, kGenFeatures)) return 1;
     for (int i = 0; i < kStages; ++i) {
         const StageW& st = h->stage[i];
-        const int P = pad64(c);
+        const int P = c;  // dense rows
         const int R = n_clips * slot;
         for (int u = 0; u < 3; ++u) {
             ENC_RUN(snake(h, h->x[i], rows, slot, n_clips, P, st.unit[u].act0, h->a[i], s));
-            ENC_RUN(launch_gemm(conv_call(h, h->a[i], R, P, st.unit[u].conv7, P, 7, kDil[u], h->hb[i], true, P, nullptr, kActNone), s));
+            ENC_RUN(launch_gemm(conv_call(h, h->a[i], R, P, st.unit[u].conv7, P, 7, kDil[u], h->hb[i], true, nullptr, kActNone), s));
             ENC_RUN(snake(h, h->hb[i], rows, slot, n_clips, P, st.unit[u].act2, h->a[i], s));
-            ENC_RUN(launch_gemm(conv_call(h, h->a[i], R, P, st.unit[u].conv1, P, 1, 1, h->x[i], true, P, h->x[i], kActNone), s));
+            ENC_RUN(launch_gemm(conv_call(h, h->a[i], R, P, st.unit[u].conv1, P, 1, 1, h->x[i], true, h->x[i], kActNone), s));
         }
         ENC_RUN(snake(h, h->x[i], rows, slot, n_clips, P, st.act, h->a[i], s));
-        const int sdn = kStrides[i], P2 = pad64(2 * c);
+        const int sdn = kStrides[i], P2 = 2 * c;
         // the same operand buffer viewed as [rows / s][s * P]: a 3-tap conv over super-rows
-        ENC_RUN(launch_gemm(conv_call(h, h->a[i], R / sdn, sdn * P, st.down, P2, 3, 1, h->x[i + 1], true, P2, nullptr, kActNone), s));
+        ENC_RUN(launch_gemm(conv_call(h, h->a[i], R / sdn, sdn * P, st.down, P2, 3, 1, h->x[i + 1], true, nullptr, kActNone), s));
         rows /= sdn;
         slot /= sdn;
         c *= 2;
@@ -838,9 +849,9 @@ int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t 
                                     static_cast<__half*>(h->s16a), h->row_valid));
     h->launches++;
     {
-        const int P = pad64(c);  // 1536
+        const int P = c;  // 1536
         ENC_RUN(snake(h, h->x[kStages], rows, slot, n_clips, P, h->act_final, h->a[kStages], s));
-        GemmCall g = conv_call(h, h->a[kStages], Rtok, P, h->conv_final, kOutDim, 3, 1, h->ac32, true, kOutDim, nullptr, kActNone);
+        GemmCall g = conv_call(h, h->a[kStages], Rtok, P, h->conv_final, kOutDim, 3, 1, h->ac32, true, nullptr, kActNone);
         g.out16 = static_cast<uint8_t*>(h->cat16) + 1024 * es;  // right half of [semantic | acoustic]
         g.ld16 = 2048;
         ENC_RUN(launch_gemm(g, s));
@@ -849,22 +860,22 @@ int b200enc_encode_batch(B200Enc* h, const float* wav_dev, int n_clips, int64_t 
     // outputs that feed the next 3-tap conv keep their gap rows zero (row_valid), like the decoder's halo rows ----
     {
         const uint8_t* rv = h->row_valid;
-        GemmCall g0 = conv_call(h, h->s16a, Rtok, 1024, h->sem_init, 1024, 3, 1, h->sr, true, 1024, nullptr, kActRelu, rv);
+        GemmCall g0 = conv_call(h, h->s16a, Rtok, 1024, h->sem_init, 1024, 3, 1, h->sr, true, nullptr, kActRelu, rv);
         g0.out16 = h->s16b;  // r = relu(initial_conv(x)) as fp32 (skip) and as operand
         g0.ld16 = 1024;
         ENC_RUN(launch_gemm(g0, s));
-        ENC_RUN(launch_gemm(conv_call(h, h->s16b, Rtok, 1024, h->sem_rb1, 1024, 3, 1, h->s16a, false, 1024, nullptr, kActRelu, rv), s));
-        GemmCall g2 = conv_call(h, h->s16a, Rtok, 1024, h->sem_rb3, 1024, 3, 1, h->sx, true, 1024, h->sr, kActNone, rv);
+        ENC_RUN(launch_gemm(conv_call(h, h->s16b, Rtok, 1024, h->sem_rb1, 1024, 3, 1, h->s16a, false, nullptr, kActRelu, rv), s));
+        GemmCall g2 = conv_call(h, h->s16a, Rtok, 1024, h->sem_rb3, 1024, 3, 1, h->sx, true, h->sr, kActNone, rv);
         g2.out16 = h->s16b;
         g2.ld16 = 1024;
         ENC_RUN(launch_gemm(g2, s));
-        GemmCall g3 = conv_call(h, h->s16b, Rtok, 1024, h->sem_final, 1024, 3, 1, h->sem32, true, 1024, nullptr, kActNone);
+        GemmCall g3 = conv_call(h, h->s16b, Rtok, 1024, h->sem_final, 1024, 3, 1, h->sem32, true, nullptr, kActNone);
         g3.out16 = h->cat16;  // left half of [semantic | acoustic]
         g3.ld16 = 2048;
         ENC_RUN(launch_gemm(g3, s));
     }
     // ---- fusion + quantise ----
-    ENC_RUN(launch_gemm(conv_call(h, h->cat16, Rtok, 2048, h->fusion, 2048, 1, 1, h->hid32, true, 2048, nullptr, kActNone), s));
+    ENC_RUN(launch_gemm(conv_call(h, h->cat16, Rtok, 2048, h->fusion, 2048, 1, 1, h->hid32, true, nullptr, kActNone), s));
     // results leave the slotted row space: one strided copy per output (clip b: rows [b * slot_tok, b * slot_tok + T))
     auto compact = [&](void* dst, const void* src, size_t row_bytes) -> int {
         B200_CUDA_OK(cudaMemcpy2DAsync(dst, static_cast<size_t>(T) * row_bytes, src, static_cast<size_t>(slot_tok) * row_bytes,
@@ -907,7 +918,7 @@ int b200enc_read_stage(B200Enc* h, const char* name, int64_t n_samples, float* h
         slot /= kStrides[i];
         c *= 2;
     }
-    const int P = pad64(c);
+    const int P = c;  // dense rows
     const size_t per_clip = static_cast<size_t>(rows) * c;
     B200_CHECK(per_clip * h->tap_clips == n_elems, "read_stage %s: expected %d x %lld x %d elements, got %zu", name,
                h->tap_clips, (long long)rows, c, n_elems);

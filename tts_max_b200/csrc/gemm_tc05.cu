@@ -208,8 +208,12 @@ int fill_params(const GemmCall& c, GemmParams* out) {
                "gemm: unsupported precision %d", c.precision);
     const int block_k = 64;
     B200_CHECK(c.Cin % block_k == 0, "gemm: Cin (%d) must be a multiple of %d", c.Cin, block_k);
-    B200_CHECK(c.n_store % 32 == 0 && c.n_store <= c.ldc, "gemm: bad n_store %d (ldc %d)",
+    B200_CHECK(c.n_store % 32 == 0 && (c.out_cols > 0 ? c.out_cols : c.n_store) <= c.ldc, "gemm: bad n_store %d (ldc %d)",
                c.n_store, c.ldc);
+    B200_CHECK(c.a_cols >= 0 && c.a_cols <= c.Cin && c.out_cols >= 0 && c.out_cols <= c.n_store && c.a_cols % 8 == 0 &&
+                   c.out_cols % 8 == 0, "gemm: bad a_cols %d / out_cols %d", c.a_cols, c.out_cols);
+    B200_CHECK(c.out_cols == 0 || (c.out16 == nullptr && c.ss_out == nullptr && c.gn_stats == nullptr),
+               "gemm: out_cols is for plain epilogues");
     B200_CHECK(c.taps >= 1 && (c.tap_pad >= 0 || c.taps % 2 == 1), "gemm: even tap counts need an explicit tap_pad");
     B200_CHECK(c.residual == nullptr || c.out_fp32, "gemm: a residual requires fp32 output");
     GemmParams p;
@@ -269,8 +273,10 @@ bool want_narrow(int a_rows, int n_store) {
 int fill_maps_2cta(const GemmCall& c, int block_n, CUtensorMap* ta, CUtensorMap* tb, CUtensorMap* to32,
                    CUtensorMap* to16) {
     const int dt16 = c.precision == kPrecBf16 ? kTmapBf16 : kTmapF16;
+    const int a_cols = c.a_cols > 0 ? c.a_cols : c.Cin;
+    const int o_cols = c.out_cols > 0 ? c.out_cols : c.n_store;
     if (c.tmap_a != nullptr) *ta = *static_cast<const CUtensorMap*>(c.tmap_a);
-    else if (make_tmap_2d(ta, c.a, dt16, c.a_rows, c.Cin, c.Cin, kGemmBlockM)) return 1;
+    else if (make_tmap_2d(ta, c.a, dt16, c.a_rows, a_cols, a_cols, kGemmBlockM)) return 1;
     if (c.tmap_b != nullptr && block_n == 256) *tb = *static_cast<const CUtensorMap*>(c.tmap_b);
     else if (make_tmap_2d(tb, c.w, dt16, c.N, static_cast<uint64_t>(c.taps) * c.Cin,
                           static_cast<uint64_t>(c.taps) * c.Cin, block_n / 2))
@@ -280,12 +286,12 @@ int fill_maps_2cta(const GemmCall& c, int block_n, CUtensorMap* ta, CUtensorMap*
     *to32 = *ta;  // placeholders for the map this GEMM does not use
     *to16 = *ta;
     if (c.out_fp32) {
-        if (make_tmap_box(to32, c.out, kTmapF32, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
+        if (make_tmap_box(to32, c.out, kTmapF32, c.a_rows, o_cols, c.ldc, kGemm2ChunkCols, 32)) return 1;
         if (c.out16 != nullptr &&
             make_tmap_box(to16, c.out16, dt16, c.a_rows, c.n_store, c.ld16, kGemm2ChunkCols, 32))
             return 1;
     } else {
-        if (make_tmap_box(to16, c.out, dt16, c.a_rows, c.n_store, c.ldc, kGemm2ChunkCols, 32)) return 1;
+        if (make_tmap_box(to16, c.out, dt16, c.a_rows, o_cols, c.ldc, kGemm2ChunkCols, 32)) return 1;
     }
     return 0;
 }

@@ -118,7 +118,12 @@ struct GemmCall {
     void* out;
     int out_fp32;        // 1 -> fp32 output, 0 -> operand dtype
     int ldc;
-    int n_store;         // multiple of 32, <= ldc; columns >= N get bias only (zeros)
+    int n_store;         // multiple of 64; columns >= N get bias only (zeros)
+    // Narrower-than-tile matrices (the encoder's 48 / 96-channel levels): a_cols > 0 = the columns of A that exist
+    // in memory (row pitch a_cols; TMA out-of-bounds fill pads every row with zeros up to Cin); out_cols > 0 = the
+    // columns of out / residual that exist (the TMA stores drop the rest; ldc >= out_cols instead of n_store)
+    int a_cols = 0;
+    int out_cols = 0;
     const float* bias;
     const float* residual;
     int ld_res;
