@@ -126,6 +126,15 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
                           const int32_t* seqlens_host, int n_utts, float* wav_host,
                           void* stream);
 
+/* The same without the final synchronisation, for callers that keep several batches in flight (a dataset sweep:
+ * tts/data/data_vectorizer.py's code store decoded bucket by bucket). wav_host_pinned must be page-locked,
+ * device-mapped memory: the last kernel stores the PCM straight into it. The call returns after the enqueue;
+ * the caller waits on `stream` (or an event recorded behind the call) before reading the PCM, and keeps ids_host
+ * valid until then if it is page-locked (pageable ids are staged before the call returns). */
+int b200codec_decode_host_async(B200Codec* h, const void* ids_host, int id_type,
+                                const int32_t* seqlens_host, int n_utts, float* wav_host_pinned,
+                                void* stream);
+
 /* ---- cached streaming (BASELINE config 5's shape) -----------------------------------------
  * The reference has no streaming decoder (tools/serving/inference.py:155-170 decodes once), and chunking
  * changes what the model computes. Two definitions are offered:

@@ -49,6 +49,30 @@ def test_decode_code_store_equals_single_decodes(tmp_path):
 
 
 @pytest.mark.gpu
+def test_decode_code_store_pipelined_equals_sequential(tmp_path):
+    """Two buckets in flight (async host decode into a ring of pinned buffers) give bit-identical waveforms to the
+    bucket-by-bucket sweep, in the same order; abandoning the generator half way leaves the decoder usable."""
+    rng = np.random.default_rng(7)
+    utts = [rng.integers(0, 65536, int(n)) for n in rng.integers(1, 260, 40)]
+    write_store(tmp_path, utts)
+    store = batching.CodeStore.open(str(tmp_path), "train")
+    dec = decoding.AudioDecoder(None, decoding.DecoderConfig("", 16000, 50, 320, None, None), device="cuda")
+    seq = list(batching.decode_code_store(dec, store, max_tokens=600, pipelined=False))
+    pipe = list(batching.decode_code_store(dec, store, max_tokens=600, pipelined=True))
+    assert [i for i, _ in seq] == [i for i, _ in pipe] and len(pipe) == len(utts)
+    for (i, a), (_, b) in zip(seq, pipe):
+        assert a.shape == b.shape == (1, 320 * len(utts[i])) and not b.is_pinned()
+        assert torch.equal(a, b), i
+    it = batching.decode_code_store(dec, store, max_tokens=600)
+    first = [next(it) for _ in range(3)]
+    it.close()
+    again = dict(batching.decode_code_store(dec, store, sample_ids=[first[0][0]], max_tokens=600))
+    assert torch.equal(again[first[0][0]], first[0][1])
+    with pytest.raises(ValueError):
+        dec._decoder.decode_packed_host_async(torch.zeros(4, dtype=torch.int32), [4], torch.empty(4 * 320))  # not pinned
+
+
+@pytest.mark.gpu
 def test_decode_completions_matches_reward_loop():
     g = torch.Generator().manual_seed(3)
     dec = decoding.AudioDecoder(None, decoding.DecoderConfig("", 16000, 50, 320, None, None), device="cuda")

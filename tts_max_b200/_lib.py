@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200codec_finalize_weights": (c_int, [c_void_p, c_void_p]),
     "b200codec_decode_varlen": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_decode_host": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
+    "b200codec_decode_host_async": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p]),
     "b200codec_take_id_error": (c_int, [c_void_p]),
     "b200codec_stream_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
     "b200codec_stream_destroy": (None, [c_void_p]),

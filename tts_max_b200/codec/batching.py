@@ -215,10 +215,13 @@ class CodeStore:
 
 
 def decode_code_store(
-    audio_decoder: AudioDecoder, store: CodeStore, sample_ids: Iterable[int] | None = None, max_tokens: int = 16384
+    audio_decoder: AudioDecoder, store: CodeStore, sample_ids: Iterable[int] | None = None, max_tokens: int = 16384,
+    pipelined: bool = True,
 ) -> Iterator[tuple[int, torch.Tensor]]:
     """Decodes samples of a CodeStore in length-sorted varlen buckets; yields (sample id, (1, L) float32
-    CPU waveform). The int32 codes go to the GPU as stored (no int64 widening)."""
+    CPU waveform). The int32 codes go to the GPU as stored (no int64 widening). `pipelined`: two buckets are
+    kept in flight (two pinned id / PCM buffers), so packing bucket k + 1 and copying bucket k's waveforms out of
+    the pinned buffer overlap the GPU's work; results are the same either way."""
     ids = list(range(len(store))) if sample_ids is None else [int(i) for i in sample_ids]
     lengths = {i: store.length(i) for i in ids}
     for i in ids:
@@ -226,11 +229,46 @@ def decode_code_store(
             raise ValueError(f"sample {i} has no codes")
     dec = audio_decoder._decoder
     hop = dec.samples_per_token
-    for bucket in sharding.bucket_by_length(ids, lengths, max_tokens=max_tokens):
-        seqlens = [lengths[i] for i in bucket]
-        packed = np.concatenate([store.codes[slice(*store.span(i))] for i in bucket]).astype(np.int32, copy=False)
-        wav = dec.decode_packed_host(torch.from_numpy(np.ascontiguousarray(packed)), seqlens)
+    buckets = sharding.bucket_by_length(ids, lengths, max_tokens=max_tokens)
+    if not pipelined:
+        for bucket in buckets:
+            seqlens = [lengths[i] for i in bucket]
+            packed = np.concatenate([store.codes[slice(*store.span(i))] for i in bucket]).astype(np.int32, copy=False)
+            wav = dec.decode_packed_host(torch.from_numpy(np.ascontiguousarray(packed)), seqlens)
+            off = 0
+            for i, n in zip(bucket, seqlens):
+                yield i, wav[off * hop:(off + n) * hop].view(1, -1)
+                off += n
+        return
+    ring_ids: list[torch.Tensor | None] = [None, None]
+    ring_wav: list[torch.Tensor | None] = [None, None]
+
+    def finish(pending):
+        bucket, seqlens, wav, event = pending
+        event.synchronize()
         off = 0
         for i, n in zip(bucket, seqlens):
-            yield i, wav[off * hop:(off + n) * hop].view(1, -1)
+            yield i, wav[off * hop:(off + n) * hop].clone().view(1, -1)   # pageable copy: the pinned buffer is reused
             off += n
+
+    pending = None
+    k = 0
+    for bucket in buckets:
+        seqlens = [lengths[i] for i in bucket]
+        total = sum(seqlens)
+        if ring_ids[k] is None or ring_ids[k].numel() < total:
+            ring_ids[k] = torch.empty(total + total // 4, dtype=torch.int32).pin_memory()
+            ring_wav[k] = torch.empty((total + total // 4) * hop, dtype=torch.float32).pin_memory()
+        ids_k, off = ring_ids[k][:total], 0
+        ids_np = ids_k.numpy()
+        for i, n in zip(bucket, seqlens):
+            ids_np[off:off + n] = store.codes[slice(*store.span(i))]
+            off += n
+        wav_k = ring_wav[k][:total * hop]
+        event = dec.decode_packed_host_async(ids_k, seqlens, wav_k)
+        if pending is not None:
+            yield from finish(pending)
+        pending = (bucket, seqlens, wav_k, event)
+        k ^= 1
+    if pending is not None:
+        yield from finish(pending)

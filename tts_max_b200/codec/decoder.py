@@ -416,6 +416,32 @@ class Decoder(torch.nn.Module):
                                                  ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(stream)))
         return dst if out is not None else dst.clone()
 
+    def decode_packed_host_async(self, ids: torch.Tensor, seqlens: Sequence[int], out: torch.Tensor) -> "torch.cuda.Event":
+        """`decode_packed_host` without the final synchronisation, for callers that keep several batches in
+        flight: `out` must be a PINNED float32 CPU tensor (the last kernel stores the PCM straight into it), `ids`
+        should be pinned too and must stay alive until the returned event has completed. Returns an event
+        recorded behind the decode on the current stream; `event.synchronize()` before reading `out`."""
+        handle = self._ensure_handle()
+        lib = _lib.load()
+        total = int(sum(int(t) for t in seqlens))
+        if ids.device.type != "cpu" or ids.dim() != 1 or ids.numel() != total or not ids.is_contiguous():
+            raise ValueError("ids must be a packed, contiguous 1-D CPU tensor matching seqlens")
+        if ids.dtype not in (torch.int32, torch.int64):
+            raise TypeError(f"ids must be int32 or int64, got {ids.dtype}")
+        n_out = total * self.samples_per_token
+        if (out.device.type != "cpu" or out.dtype != torch.float32 or out.numel() != n_out or not out.is_contiguous()
+                or not out.is_pinned()):
+            raise ValueError("out must be a pinned, contiguous float32 CPU tensor of hop * sum(seqlens) samples")
+        id_type = _lib.IDS_I64 if ids.dtype == torch.int64 else _lib.IDS_I32
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device)
+            _lib.check(lib.b200codec_decode_host_async(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
+                                                       _lib.i32_array(seqlens), len(seqlens),
+                                                       ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream.cuda_stream)))
+            event = torch.cuda.Event()
+            event.record(stream)
+        return event
+
     def take_id_error(self) -> bool:
         """True if a device-side decode since the last call saw an id outside [0, 65535]."""
         if self._handle is None:

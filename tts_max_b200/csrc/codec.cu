@@ -184,8 +184,17 @@ struct B200Codec {
     // plan (row space) cache; plan i > 0 is the row space after upsampler stage i - 1
     // (every length, offset and gap of plan 0 multiplied by the product of the strides so far)
     DevBuf plan_dev, plan_up_dev[kMaxUp];
-    void* plan_host = nullptr;
-    size_t plan_host_bytes = 0;
+    // page-locked staging for plan uploads: a ring, so that building the plan of the next shape does not wait for
+    // the stream (the device-side plan is rewritten in stream order; only the host staging needs a guard)
+    struct PlanStage {
+        void* host = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t copied = nullptr;
+        bool pending = false;
+    };
+    static constexpr int kPlanStages = 4;
+    PlanStage plan_stage[kPlanStages];
+    int plan_stage_next = 0;
     std::vector<int32_t> plan_key;
     int plan_gap = -1;
     int plan_istft_mode = -1;
@@ -426,45 +435,57 @@ int build_plan(B200Codec* h, const int32_t* seqlens, int n_utts, int gap, cudaSt
                 std::memcmp(h->plan_key.data(), seqlens, sizeof(int32_t) * n_utts) == 0;
     if (same) return 0;
     h->generation++;
-    PlanLayout L;
+    // layouts of the token row space and of every upsampled row space (out row = stride * in row + phase, so
+    // everything scales by the stride)
+    PlanLayout L, Lu[kMaxUp];
     if (plan_layout(seqlens, n_utts, gap, &L)) return 1;
-    if (L.total_bytes > h->plan_host_bytes) {
-        if (h->plan_host) cudaFreeHost(h->plan_host);
-        h->plan_host = nullptr;
-        h->plan_host_bytes = 0;
-        B200_CUDA_OK(cudaMallocHost(&h->plan_host, L.total_bytes * 2));
-        h->plan_host_bytes = L.total_bytes * 2;
-    }
-    // the previous plan may still be in use by work in flight on the stream
-    B200_CUDA_OK(cudaStreamSynchronize(stream));
-    if (h->plan_dev.ensure(L.total_bytes)) return 1;
-    plan_fill(L, seqlens, gap, h->plan_host);
-    B200_CUDA_OK(cudaMemcpyAsync(h->plan_dev.p, h->plan_host, L.total_bytes, cudaMemcpyHostToDevice,
-                                 stream));
-    B200_CUDA_OK(cudaStreamSynchronize(stream));  // plan_host is reused by the next build
-    plan_bind(L, h->plan_dev.p, &h->rs);
-    // upsampled row spaces: out row = stride * in row + phase, so everything scales by the stride
-    int factor = 1;
-    std::vector<int32_t> scaled(n_utts);
-    for (int i = 0; i < h->n_up; ++i) {
-        factor *= h->up_f[i];
-        for (int u = 0; u < n_utts; ++u) scaled[u] = seqlens[u] * factor;
-        PlanLayout Lu;
-        if (plan_layout(scaled.data(), n_utts, gap * factor, &Lu)) return 1;
-        if (Lu.total_bytes > h->plan_host_bytes) {
-            cudaFreeHost(h->plan_host);
-            h->plan_host = nullptr;
-            h->plan_host_bytes = 0;
-            B200_CUDA_OK(cudaMallocHost(&h->plan_host, Lu.total_bytes * 2));
-            h->plan_host_bytes = Lu.total_bytes * 2;
+    std::vector<int32_t> scaled[kMaxUp];
+    int up_gap[kMaxUp];
+    auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    size_t need = al(L.total_bytes);
+    {
+        int factor = 1;
+        for (int i = 0; i < h->n_up; ++i) {
+            factor *= h->up_f[i];
+            scaled[i].resize(n_utts);
+            for (int u = 0; u < n_utts; ++u) scaled[i][u] = seqlens[u] * factor;
+            up_gap[i] = gap * factor;
+            if (plan_layout(scaled[i].data(), n_utts, up_gap[i], &Lu[i])) return 1;
+            need += al(Lu[i].total_bytes);
         }
-        if (h->plan_up_dev[i].ensure(Lu.total_bytes)) return 1;
-        plan_fill(Lu, scaled.data(), gap * factor, h->plan_host);
-        B200_CUDA_OK(cudaMemcpyAsync(h->plan_up_dev[i].p, h->plan_host, Lu.total_bytes, cudaMemcpyHostToDevice,
-                                     stream));
-        B200_CUDA_OK(cudaStreamSynchronize(stream));
-        plan_bind(Lu, h->plan_up_dev[i].p, &h->rs_up[i]);
     }
+    // No stream synchronisation: the device plan is rewritten by copies in stream order (behind whatever still
+    // reads the previous plan); the host staging buffer comes from a ring and is only refilled once the copy that
+    // last read it has executed. (Growing a device buffer frees the old one, which waits for the device.)
+    B200Codec::PlanStage& st = h->plan_stage[h->plan_stage_next];
+    h->plan_stage_next = (h->plan_stage_next + 1) % B200Codec::kPlanStages;
+    if (st.pending) {
+        B200_CUDA_OK(cudaEventSynchronize(st.copied));
+        st.pending = false;
+    }
+    if (need > st.bytes) {
+        if (st.host) cudaFreeHost(st.host);
+        st.host = nullptr;
+        st.bytes = 0;
+        B200_CUDA_OK(cudaMallocHost(&st.host, need * 2));
+        st.bytes = need * 2;
+    }
+    if (st.copied == nullptr) B200_CUDA_OK(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
+    uint8_t* hp = static_cast<uint8_t*>(st.host);
+    if (h->plan_dev.ensure(L.total_bytes)) return 1;
+    plan_fill(L, seqlens, gap, hp);
+    B200_CUDA_OK(cudaMemcpyAsync(h->plan_dev.p, hp, L.total_bytes, cudaMemcpyHostToDevice, stream));
+    plan_bind(L, h->plan_dev.p, &h->rs);
+    hp += al(L.total_bytes);
+    for (int i = 0; i < h->n_up; ++i) {
+        if (h->plan_up_dev[i].ensure(Lu[i].total_bytes)) return 1;
+        plan_fill(Lu[i], scaled[i].data(), up_gap[i], hp);
+        B200_CUDA_OK(cudaMemcpyAsync(h->plan_up_dev[i].p, hp, Lu[i].total_bytes, cudaMemcpyHostToDevice, stream));
+        plan_bind(Lu[i], h->plan_up_dev[i].p, &h->rs_up[i]);
+        hp += al(Lu[i].total_bytes);
+    }
+    B200_CUDA_OK(cudaEventRecord(st.copied, stream));
+    st.pending = true;
     h->plan_key.assign(seqlens, seqlens + n_utts);
     h->plan_gap = gap;
     h->plan_istft_mode = g_istft_hops;
@@ -1178,7 +1199,10 @@ void b200codec_destroy(B200Codec* h) {
     for (int i = 0; i < kMaxUp; ++i) h->plan_up_dev[i].release();
     h->io_ids.release();
     h->io_wav.release();
-    if (h->plan_host) cudaFreeHost(h->plan_host);
+    for (auto& st : h->plan_stage) {
+        if (st.host) cudaFreeHost(st.host);
+        if (st.copied) cudaEventDestroy(st.copied);
+    }
     if (h->head_bias_pad) cudaFree(h->head_bias_pad);
     if (h->twiddle) cudaFree(h->twiddle);
     if (h->m_fold) cudaFree(h->m_fold);
@@ -1690,6 +1714,35 @@ int b200codec_decode_host(B200Codec* h, const void* ids_host, int id_type,
     }
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
+}
+
+// Same with page-locked buffers and WITHOUT the final synchronisation: the PCM is stored straight into the
+// mapped host buffer by the last kernel, the call returns after the enqueue, and the caller waits on the stream
+// (or on an event recorded behind the call) before reading wav_host. A dataset sweep keeps two buffers in flight,
+// so the host-side handling of batch k (copies, resampling, file writes) overlaps the decode of batch k + 1.
+int b200codec_decode_host_async(B200Codec* h, const void* ids_host, int id_type, const int32_t* seqlens_host,
+                                int n_utts, float* wav_host_pinned, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CHECK(h && ids_host && wav_host_pinned && seqlens_host, "decode_host_async: null argument");
+    B200_CHECK(n_utts > 0, "decode: empty batch (no utterances)");
+    int64_t toks = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        B200_CHECK(seqlens_host[u] > 0, "decode: utterance %d is empty", u);
+        toks += seqlens_host[u];
+    }
+    if (check_ids_host(ids_host, id_type, toks)) return 1;
+    std::lock_guard<std::mutex> lock(h->mu);
+    B200_CUDA_OK(cudaSetDevice(h->cfg.device));
+    cudaPointerAttributes attr;
+    const bool mapped = cudaPointerGetAttributes(&attr, wav_host_pinned) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                        attr.devicePointer != nullptr;
+    if (!mapped) (void)cudaGetLastError();
+    B200_CHECK(mapped, "decode_host_async: wav_host must be page-locked, device-mapped memory (cudaHostAlloc / pin_memory)");
+    const size_t id_bytes = static_cast<size_t>(toks) * (id_type == B200CODEC_IDS_I64 ? 8 : 4);
+    if (id_bytes > h->io_ids.bytes) B200_CUDA_OK(cudaStreamSynchronize(s));  // a previous call may still read the old buffer
+    if (h->io_ids.ensure(id_bytes)) return 1;
+    B200_CUDA_OK(cudaMemcpyAsync(h->io_ids.p, ids_host, id_bytes, cudaMemcpyHostToDevice, s));
+    return decode_varlen_locked(h, h->io_ids.p, id_type, seqlens_host, n_utts, static_cast<float*>(attr.devicePointer), s);
 }
 
 int b200codec_samples_per_token(const B200Codec* h) { return h ? h->hop * h->total_up : 0; }
