@@ -58,7 +58,7 @@ enum B200CodecDType { B200CODEC_F32 = 0, B200CODEC_F16 = 1, B200CODEC_BF16_T = 2
 typedef struct B200CodecConfig {
     int32_t abi_version;      /* must be B200CODEC_ABI_VERSION */
     int32_t sample_rate;      /* 16000 for xcodec2 */
-    int32_t hop_length;       /* 320 (xcodec2) or 160 (48 kHz); n_fft = win = 4 * hop (decoder_modules.py:426-431) */
+    int32_t hop_length;       /* 320 (xcodec2), 160 (48 kHz), also 240 and 80; n_fft = win = 4 * hop (decoder_modules.py:426-431) */
     int32_t n_upsample;       /* len(upsample_factors): 0 (xcodec2) .. 3 (UpSamplerBlock, upsampler.py:9-69) */
     int32_t precision;        /* enum B200CodecPrecision */
     int32_t device;           /* CUDA device ordinal */

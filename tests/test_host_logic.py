@@ -40,7 +40,10 @@ def test_rate_check_matches_reference():
     with pytest.raises(ValueError, match="do not match the target"):
         decoder.Decoder(48000, 160, [3, 2, 2], [7, 6, 4])
     with pytest.raises(NotImplementedError):
-        decoder.Decoder(96000, 160, [3, 2, 2], [7, 6, 4])  # three stages are not instantiated
+        decoder.Decoder(192000, 160, [3, 2, 2, 2], [7, 6, 4, 4])  # four stages (64 channels) are not instantiated
+    with pytest.raises(NotImplementedError):
+        decoder.Decoder(4800, 96, None, None)  # n_fft 384 is not 64 x (a multiple of 5)
+    assert decoder.Decoder(96000, 160, [3, 2, 2], [7, 6, 4], init_seed=0).samples_per_token == 1920  # three stages
     d = decoder.Decoder(48000, 160, [3, 2], [7, 6], init_seed=0)  # the 48 kHz upsampler variant
     assert d.samples_per_token == 960 and len(d.state_dict()) == 145
 

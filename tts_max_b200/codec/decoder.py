@@ -189,12 +189,12 @@ class Decoder(torch.nn.Module):
         if self.upsample_factors:
             if not self.kernel_sizes or len(self.kernel_sizes) != len(self.upsample_factors):
                 raise ValueError("kernel_sizes must match upsample_factors")
-            if len(self.upsample_factors) > 2 or any((k - u) % 2 or k < u for k, u in zip(self.kernel_sizes, self.upsample_factors)):
+            if len(self.upsample_factors) > 3 or any((k - u) % 2 or k < u for k, u in zip(self.kernel_sizes, self.upsample_factors)):
                 raise NotImplementedError(
                     f"upsampler configuration factors={self.upsample_factors} kernels={self.kernel_sizes} is not "
-                    "instantiated (at most two stages, kernel - factor even)")
-        if self.hop_length not in (320, 160):
-            raise NotImplementedError("only hop_length 320 (n_fft 1280) and 160 (n_fft 640) are instantiated")
+                    "instantiated (at most three stages: 512 / 256 / 128 channels; kernel - factor even)")
+        if self.hop_length not in (320, 240, 160, 80):
+            raise NotImplementedError("hop_length must be 320, 240, 160 or 80 (n_fft = 4 hop = 64 x {20, 15, 10, 5})")
         self.samples_per_token = self.hop_length * total_ups
 
         self._shapes = expected_state_dict_shapes(hop_length, DEPTH, self.upsample_factors, self.kernel_sizes)

@@ -1105,9 +1105,9 @@ int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
     B200_CHECK(cfg != nullptr && out != nullptr, "b200codec_create: null argument");
     B200_CHECK(cfg->abi_version == B200CODEC_ABI_VERSION, "ABI version mismatch: caller %d, library %d",
                cfg->abi_version, B200CODEC_ABI_VERSION);
-    B200_CHECK(cfg->n_upsample >= 0 && cfg->n_upsample <= 2,
-               "upsample_factors: %d stages are not supported (0, 1 or 2; channels halve per stage and the "
-               "kernels are instantiated for 512 and 256)", cfg->n_upsample);
+    B200_CHECK(cfg->n_upsample >= 0 && cfg->n_upsample <= 3,
+               "upsample_factors: %d stages are not supported (0 .. 3; channels halve per stage and the "
+               "kernels are instantiated for 512, 256 and 128)", cfg->n_upsample);
     int total_up = 1;
     for (int i = 0; i < cfg->n_upsample; ++i) {
         const int u = cfg->upsample_factors[i], k = cfg->kernel_sizes[i];
@@ -1119,8 +1119,8 @@ int b200codec_create(const B200CodecConfig* cfg, B200Codec** out) {
     B200_CHECK(cfg->hop_length > 0 && cfg->sample_rate / cfg->hop_length / total_up == 50,
                "Current hop length %d and upsample factors (product %d) do not match the target sample "
                "rate %d.", cfg->hop_length, total_up, cfg->sample_rate);  // decoder.py:31-37
-    B200_CHECK(cfg->hop_length == 320 || cfg->hop_length == 160,
-               "only hop_length 320 (n_fft 1280) and 160 (n_fft 640) are instantiated");
+    B200_CHECK(cfg->hop_length == 320 || cfg->hop_length == 240 || cfg->hop_length == 160 || cfg->hop_length == 80,
+               "hop_length %d is not instantiated (320, 240, 160, 80: n_fft = 4 hop = 64 x {20, 15, 10, 5})", cfg->hop_length);
     B200_CHECK(cfg->precision == B200CODEC_BF16 || cfg->precision == B200CODEC_FP16,
                "precision %d is not available (bf16 = 0, fp16 = 1)", cfg->precision);
     B200_CHECK(cfg->hidden_dim == 1024 && cfg->heads == 16 && cfg->vq_dim == 2048 &&

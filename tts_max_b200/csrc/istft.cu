@@ -82,13 +82,25 @@ __device__ __forceinline__ void idft8(float2 (&v)[8]) {
     v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
     v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
-// Prime-factor inverse DFT of length N1 = NA * 5 (NA = 4 or 2; gcd(NA, 5) = 1, so no twiddles):
-// input index n = (5 a + NA b) mod N1, output index k = (5 ka + NA (NA^-1 mod 5) kb) mod N1.
+__device__ __forceinline__ void idft3(float2& x0, float2& x1, float2& x2) {
+    // out[q] = sum_r x[r] w^(q r), w = exp(+2 pi i / 3) = -1/2 + i sqrt(3)/2
+    constexpr float h = 0.8660254037844386f;
+    const float2 sum = cadd(x1, x2);
+    const float2 d = cmuli(__fmul2_rn(make_float2(h, h), csub(x1, x2)));
+    const float2 t = cfma(-0.5f, sum, x0);
+    x0 = cadd(x0, sum);
+    x1 = cadd(t, d);
+    x2 = csub(t, d);
+}
+// Prime-factor inverse DFT of length N1 = NA * 5 (NA = 4, 3, 2 or 1; gcd(NA, 5) = 1, so no twiddles):
+// input index n = (5 a + NA b) mod N1, output index k = (KA ka + KB kb) mod N1 with KA = 5 (5^-1 mod NA),
+// KB = NA (NA^-1 mod 5) (the CRT map).
 template <int N1>
 __device__ __forceinline__ void idft_pfa(float2 (&v)[N1]) {
-    static_assert(N1 == 20 || N1 == 10, "DFT-20 (4 x 5) and DFT-10 (2 x 5)");
+    static_assert(N1 == 20 || N1 == 15 || N1 == 10 || N1 == 5, "DFT-20 (4 x 5), DFT-15 (3 x 5), DFT-10 (2 x 5), DFT-5");
     constexpr int NA = N1 / 5;
-    constexpr int KB = NA == 4 ? 16 : 6;  // NA * (NA^-1 mod 5)
+    constexpr int KA = NA == 3 ? 10 : 5;
+    constexpr int KB = NA == 4 ? 16 : NA == 3 ? 6 : NA == 2 ? 6 : 1;
     float2 y[NA][5];
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
@@ -100,13 +112,15 @@ __device__ __forceinline__ void idft_pfa(float2 (&v)[N1]) {
     for (int kb = 0; kb < 5; ++kb) {
         if constexpr (NA == 4) {
             idft4(y[0][kb], y[1][kb], y[2][kb], y[3][kb]);
-        } else {
+        } else if constexpr (NA == 3) {
+            idft3(y[0][kb], y[1][kb], y[2][kb]);
+        } else if constexpr (NA == 2) {
             const float2 s = cadd(y[0][kb], y[1][kb]), d = csub(y[0][kb], y[1][kb]);
             y[0][kb] = s;
             y[1][kb] = d;
         }
 #pragma unroll
-        for (int ka = 0; ka < NA; ++ka) v[(5 * ka + KB * kb) % N1] = y[ka][kb];
+        for (int ka = 0; ka < NA; ++ka) v[(KA * ka + KB * kb) % N1] = y[ka][kb];
     }
 }
 
@@ -117,7 +131,8 @@ template <int HOP>
 struct IstftCfg {
     static constexpr int kN = 4 * HOP;        // n_fft = complex FFT length (two real frames per transform)
     static constexpr int kBins = 2 * HOP + 1;
-    static constexpr int kN1 = kN / 64;       // 20 or 10
+    static constexpr int kN1 = kN / 64;       // 20, 15, 10 or 5 (hop 320, 240, 160, 80)
+    static_assert(kN % 64 == 0 && kN1 % 5 == 0, "n_fft = 4 hop must be 64 x (a multiple of 5)");
     static constexpr int kCombos = 8 * kN1;   // (k1, n3) / (k1, k2) combinations of the radix-8 steps
     static constexpr int kRounds = (kCombos + 31) / 32;
     static constexpr int kScratch = kN1 * kT1Stride;  // float2 words per warp: T1 == T2 size >= 2 * kBins, >= kN
@@ -210,7 +225,9 @@ istft_kernel(const float* __restrict__ x_pred, int ld, const int4* __restrict__ 
 #pragma unroll
             for (int n1 = 0; n1 < kN1; ++n1) {
                 const int n = 64 * n1 + c;
-                if (n1 < kN1 / 2) {  // n < N/2: the bin itself
+                // N / 2 = 32 N1: for odd N1 it falls inside block n1 = N1 / 2, whose low offsets (c < 32) are bins
+                // and whose high offsets (c >= 32) are mirrors
+                if (n1 < kN1 / 2 || (kN1 % 2 == 1 && n1 == kN1 / 2 && o == 0)) {  // n < N/2: the bin itself
                     const float2 xa = sc[n], xb = sc[kBins + n];
                     y[o][n1] = make_float2(xa.x - xb.y, xa.y + xb.x);
                 } else {             // n >= N/2: conj of bin N - n
@@ -376,7 +393,15 @@ int launch_istft(const float* x_pred, int ld, const RowSpace& rs, const IstftTab
         if (rs.istft_hops == 12) return launch_istft_typed<160, 8>(x_pred, ld, rs, tab, wav, stream);
         return launch_istft_typed<160, 16>(x_pred, ld, rs, tab, wav, stream);
     }
-    set_error("istft: hop_length %d is not instantiated (320: n_fft 1280, 160: n_fft 640)", hop);
+    if (hop == 240) {
+        if (rs.istft_hops == 12) return launch_istft_typed<240, 8>(x_pred, ld, rs, tab, wav, stream);
+        return launch_istft_typed<240, 16>(x_pred, ld, rs, tab, wav, stream);
+    }
+    if (hop == 80) {
+        if (rs.istft_hops == 12) return launch_istft_typed<80, 8>(x_pred, ld, rs, tab, wav, stream);
+        return launch_istft_typed<80, 16>(x_pred, ld, rs, tab, wav, stream);
+    }
+    set_error("istft: hop_length %d is not instantiated (320, 240, 160, 80: n_fft = 4 hop = 64 x {20, 15, 10, 5})", hop);
     return 1;
 }
 

@@ -190,7 +190,10 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
     const int t = threadIdx.x % kTpr;
     const int sub = threadIdx.x / kTpr;
     const int c0 = t * 8;
-    const int group = c0 / (DIM / 32);  // a thread's 8 channels never straddle a group (group size >= 8)
+    // group size DIM / 32 >= 8: a thread's 8 channels sit in one group; DIM = 128 (groups of 4): in two
+    constexpr bool kTwoGroups = DIM / 32 < 8;
+    static_assert(DIM / 32 >= 4, "GroupNorm(32) kernels: at least 128 channels");
+    const int group = c0 / (DIM / 32);
     float g[8], b[8];
     {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
@@ -207,7 +210,7 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
     const int r_lo = blockIdx.x * slab;
     const int r_hi = min(r_lo + slab, rows);
     int cur_u = -1;
-    float2 mr = make_float2(0.f, 0.f);
+    float2 mr = make_float2(0.f, 0.f), mr2 = mr;  // (mean, rstd) of the group(s) of this thread's channels
     // two rows per step with all four 128-bit loads issued before anything depends on them (the
     // pass is HBM-bound: bytes in flight per thread are what it needs)
     auto finish_row = [&](int r, int u, const float4& v0, const float4& v1) {
@@ -216,15 +219,20 @@ groupnorm_apply_swish_kernel(const float* __restrict__ x, const int32_t* __restr
             if (u != cur_u) {
                 cur_u = u;
                 const double cnt = static_cast<double>(utt_len[u]) * (DIM / 32);
-                const double m = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 0] / cnt;
-                double var = stats[(static_cast<size_t>(u) * 32 + group) * 2 + 1] / cnt - m * m;
-                var = var < 0.0 ? 0.0 : var;
-                mr = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+                auto mean_rstd = [&](int grp) {
+                    const double m = stats[(static_cast<size_t>(u) * 32 + grp) * 2 + 0] / cnt;
+                    double var = stats[(static_cast<size_t>(u) * 32 + grp) * 2 + 1] / cnt - m * m;
+                    var = var < 0.0 ? 0.0 : var;
+                    return make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+                };
+                mr = mean_rstd(group);
+                mr2 = kTwoGroups ? mean_rstd(group + 1) : mr;
             }
             float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float n = (y[j] - mr.x) * mr.y * g[j] + b[j];
+                const float2 q = (kTwoGroups && j >= 4) ? mr2 : mr;
+                const float n = (y[j] - q.x) * q.y * g[j] + b[j];
                 y[j] = __fdividef(n, 1.f + __expf(-n));  // x * sigmoid(x)
             }
             packed.x = Half16<OutT>::pack(y[0], y[1]);
@@ -287,8 +295,9 @@ int launch_gn_dispatch(int dim, int prec, const float* x, const RowSpace& rs, co
         case 1024: return launch_gn_typed<1024>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
         case 512: return launch_gn_typed<512>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
         case 256: return launch_gn_typed<256>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
+        case 128: return launch_gn_typed<128>(prec, x, rs, stats, gamma, beta, eps, out, stream, stats_only, stats_out);
         default:
-            set_error("groupnorm: dim %d is not instantiated (1024, 512, 256)", dim);
+            set_error("groupnorm: dim %d is not instantiated (1024, 512, 256, 128)", dim);
             return 1;
     }
 }
