@@ -229,6 +229,37 @@ def test_large_batch_index_math(gpu_decoders):
     torch.cuda.empty_cache()
 
 
+def test_concurrent_callers_share_a_decoder(gpu_decoders):
+    """Two threads on ONE decoder (ctypes releases the GIL; the handle's mutex serialises them) and on two decoders:
+    every result is the one the utterance gets alone."""
+    import threading
+    shared = gpu_decoders["bf16"]
+    other = gpu_decoders["fp16"]
+    g = torch.Generator().manual_seed(77)
+    utts = [torch.randint(0, 65536, (t,), generator=g) for t in (31, 250, 7, 129, 64, 300)]
+    want = {id(d): [d.decode_packed_host(u, [u.numel()]) for u in utts] for d in (shared, other)}
+    errors = []
+
+    def worker(d, order):
+        try:
+            for _ in range(6):
+                for k in order:
+                    got = d.decode_packed_host(utts[k], [utts[k].numel()])
+                    if not torch.equal(got, want[id(d)][k]):
+                        errors.append((id(d), k))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(shared, [0, 1, 2, 3, 4, 5])),
+               threading.Thread(target=worker, args=(shared, [5, 3, 1, 4, 2, 0])),
+               threading.Thread(target=worker, args=(other, [2, 0, 5, 1, 3, 4]))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:4]
+
+
 def test_config2_vs_oracle_subsample(gpu_decoders, state_dict):
     """BASELINE config 2 (16 x 10 s, bf16): two of the sixteen clips checked against the oracle."""
     ids = torch.randint(0, 65536, (16, 500), generator=torch.Generator().manual_seed(1234))

@@ -14,6 +14,7 @@ import collections
 import ctypes
 import logging
 import math
+import threading
 from typing import Any, Iterable, Sequence
 
 import torch
@@ -203,6 +204,7 @@ class Decoder(torch.nn.Module):
             hop_length, init_seed, self.upsample_factors, self.kernel_sizes)
         self._handle: ctypes.c_void_p | None = None
         self._pinned_out: torch.Tensor | None = None
+        self._pinned_lock = threading.Lock()  # the staging buffer is shared by the callers of decode_packed_host
         self._device: torch.device = torch.device("cpu")
         self._dirty = True
 
@@ -311,6 +313,12 @@ class Decoder(torch.nn.Module):
                 f"fallback; call .to('cuda') first (current device: {self._device})"
             )
         lib = _lib.load()
+        if self._handle is not None and not self._dirty:
+            return self._handle
+        with self._pinned_lock:  # first use from several threads: create / load once
+            return self._ensure_handle_locked(lib)
+
+    def _ensure_handle_locked(self, lib) -> ctypes.c_void_p:
         if self._handle is None:
             ups = list(self.upsample_factors or [])
             ks = list(self.kernel_sizes or []) if ups else []
@@ -400,21 +408,28 @@ class Decoder(torch.nn.Module):
             if out.device.type != "cpu" or out.dtype != torch.float32 or out.numel() != n_out or not out.is_contiguous():
                 raise ValueError("out must be a contiguous float32 CPU tensor of hop * sum(seqlens) samples")
             dst = out
-        else:
-            # One page-locked staging buffer per decoder (grow-only): the last kernel stores the PCM
-            # straight into it (zero-copy). Callers get a pageable copy, so accumulating results (a
-            # dataset sweep) never pins an unbounded amount of host memory; pass `out=` (ideally a
-            # pinned tensor the caller reuses) to skip the copy.
+            with torch.cuda.device(self._device):
+                stream = torch.cuda.current_stream(self._device).cuda_stream
+                _lib.check(lib.b200codec_decode_host(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
+                                                     _lib.i32_array(seqlens), len(seqlens),
+                                                     ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(stream)))
+            return dst
+        # One page-locked staging buffer per decoder (grow-only): the last kernel stores the PCM
+        # straight into it (zero-copy). Callers get a pageable copy, so accumulating results (a
+        # dataset sweep) never pins an unbounded amount of host memory; pass `out=` (ideally a
+        # pinned tensor the caller reuses) to skip the copy. The lock covers decode + copy: the C call
+        # releases the GIL, and another thread's decode would overwrite the staging buffer before the copy.
+        with self._pinned_lock:
             if self._pinned_out is None or self._pinned_out.numel() < n_out:
                 self._pinned_out = None
                 self._pinned_out = torch.empty(n_out + n_out // 4, dtype=torch.float32, pin_memory=True)
             dst = self._pinned_out[:n_out]
-        with torch.cuda.device(self._device):
-            stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(lib.b200codec_decode_host(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
-                                                 _lib.i32_array(seqlens), len(seqlens),
-                                                 ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(stream)))
-        return dst if out is not None else dst.clone()
+            with torch.cuda.device(self._device):
+                stream = torch.cuda.current_stream(self._device).cuda_stream
+                _lib.check(lib.b200codec_decode_host(handle, ctypes.c_void_p(ids.data_ptr()), id_type,
+                                                     _lib.i32_array(seqlens), len(seqlens),
+                                                     ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(stream)))
+            return dst.clone()
 
     def decode_packed_host_async(self, ids: torch.Tensor, seqlens: Sequence[int], out: torch.Tensor) -> "torch.cuda.Event":
         """`decode_packed_host` without the final synchronisation, for callers that keep several batches in
